@@ -1,0 +1,106 @@
+// CPU thread-emulation harness for the per-CTA phase functions of the CUDA
+// kernels (TEST INFRASTRUCTURE ONLY -- compiled and loaded by tests/, never by
+// the product).  It includes the very same headers the kernels are built from
+// and runs each phase for tid = 0..nthreads-1 where the kernel has a
+// __syncthreads(), so index arithmetic, scramble tables and twiddles can be
+// checked against the oracle on a machine without a GPU.
+#include <vector>
+#include <cstring>
+#include "../../transport_analysis_b200/csrc/ta_common.cuh"
+#include "../../transport_analysis_b200/csrc/fft_plan.h"
+#include "../../transport_analysis_b200/csrc/fft_core.cuh"
+#include "../../transport_analysis_b200/csrc/windowed_core.cuh"
+
+using namespace ta;
+
+template <typename R>
+static int run_fft(const double* series, int T, int D, int Tld, int nthr, double* row, double* partial) {
+    FftPlanHost hp;
+    int rc = ta_build_fft_plan(T, &hp);
+    if (rc) return rc;
+    int nlo = 1 << hp.lo_bits, nhi = (int)hp.tw_hi.size() / 2;
+    std::vector<cplx<R>> lo(nlo), hi(nhi);
+    for (int i = 0; i < nlo; ++i) lo[i] = cmake<R>((R)hp.tw_lo[2 * i], (R)hp.tw_lo[2 * i + 1]);
+    for (int i = 0; i < nhi; ++i) hi[i] = cmake<R>((R)hp.tw_hi[2 * i], (R)hp.tw_hi[2 * i + 1]);
+    std::vector<uint32_t> own0;
+    for (int p = 0; p < hp.H; ++p) if ((uint32_t)p <= hp.pair0[p]) own0.push_back(p);
+    FftTables<R> t;
+    t.T = T; t.H = hp.H; t.L = hp.L; t.npasses = hp.npasses;
+    for (int i = 0; i < hp.npasses; ++i) t.radix[i] = hp.radix[i];
+    t.lo_bits = hp.lo_bits; t.tw_lo = lo.data(); t.tw_hi = hi.data();
+    t.ftab = hp.ftab.data(); t.pair0 = hp.pair0.data(); t.own0 = own0.data(); t.npairs0 = (int)own0.size();
+    std::vector<cplx<R>> buf(hp.H);
+    std::vector<R> sd(hp.H + 1);
+#define PHASE(call) for (int tid = 0; tid < nthr; ++tid) { call; }
+    for (int r = 0; r < 2; ++r) {
+        PHASE(fft_zero_acc<R>(tid, nthr, sd.data(), t));
+        for (int d = 0; d < D; ++d) {
+            PHASE(fft_load<R>(tid, nthr, buf.data(), series + (size_t)d * Tld, t, r));
+            int size = t.H;
+            for (int ps = 0; ps < t.npasses; ++ps) {
+                int s = size / t.radix[ps];
+                PHASE(dif_pass_any<R>(t.radix[ps], tid, nthr, buf.data(), t, s));
+                size = s;
+            }
+            PHASE(fft_accumulate<R>(tid, nthr, buf.data(), sd.data(), t, r));
+        }
+        PHASE(fft_build<R>(tid, nthr, buf.data(), sd.data(), t, r));
+        int s = 1;
+        for (int ps = t.npasses - 1; ps >= 0; --ps) {
+            PHASE(dit_pass_any<R>(t.radix[ps], tid, nthr, buf.data(), t, s));
+            s *= t.radix[ps];
+        }
+        PHASE(fft_store<R>(tid, nthr, buf.data(), row, partial, t, r));
+    }
+    return 0;
+}
+
+template <typename R>
+static int run_win(const double* series, int T, int D, int Tld, int mode, int nwarps, double* res) {
+    int ne = win_smem_elems(T);
+    std::vector<R> S(ne);
+    int nlb = win_num_lag_blocks(T), npairs = win_num_pairs(nlb);
+    for (int k = 0; k < T; ++k) res[k] = 0.0;
+    for (int d = 0; d < D; ++d) {
+        std::fill(S.begin(), S.end(), (R)0);
+        for (int x = 0; x < T; ++x) S[win_addr(x)] = (R)series[(size_t)d * Tld + x];
+        for (int w = 0; w < nwarps; ++w) {
+            for (int pair = w; pair < npairs; pair += nwarps) {
+                int kbs[2];
+                win_pair_blocks(pair, nlb, &kbs[0], &kbs[1]);
+                for (int h = 0; h < 2; ++h) {
+                    int kb = kbs[h];
+                    if (kb < 0) continue;
+                    R tot[16] = {0};
+                    for (int lane = 0; lane < 32; ++lane) {
+                        R acc[16] = {0};
+                        if (mode == TA_WIN_PRODUCT) win_lane_accumulate<R, TA_WIN_PRODUCT>(lane, 32, S.data(), T, kb, acc);
+                        else win_lane_accumulate<R, TA_WIN_SQDIFF>(lane, 32, S.data(), T, kb, acc);
+                        for (int m = 0; m < 16; ++m) tot[m] += acc[m];
+                    }
+                    for (int m = 0; m < 16; ++m) if (kb * 16 + m < T) res[kb * 16 + m] += (double)tot[m];
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+extern "C" {
+int emu_fft_acf(const double* series, int T, int D, int Tld, int nthr, int use_f32, double* row, double* partial) {
+    return use_f32 ? run_fft<float>(series, T, D, Tld, nthr, row, partial)
+                   : run_fft<double>(series, T, D, Tld, nthr, row, partial);
+}
+int emu_windowed(const double* series, int T, int D, int Tld, int mode, int nwarps, int use_f32, double* res) {
+    return use_f32 ? run_win<float>(series, T, D, Tld, mode, nwarps, res)
+                   : run_win<double>(series, T, D, Tld, mode, nwarps, res);
+}
+int emu_plan(int T, int* H, int* npasses, int* radix) {
+    FftPlanHost hp;
+    int rc = ta_build_fft_plan(T, &hp);
+    if (rc) return rc;
+    *H = hp.H; *npasses = hp.npasses;
+    for (int i = 0; i < hp.npasses; ++i) radix[i] = hp.radix[i];
+    return 0;
+}
+}

@@ -1,0 +1,84 @@
+"""The kernels' per-CTA phase functions (fft_core.cuh, windowed_core.cuh),
+compiled for the CPU by tests/emu and run phase by phase, against the oracle.
+This is what checks index arithmetic, scramble tables and twiddles in the
+container that has no GPU; the GPU parity tests are in test_gpu_parity.py."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import oracle
+from _util import assert_close_normwise
+
+DP = ctypes.POINTER(ctypes.c_double)
+
+
+def _p(a):
+    return a.ctypes.data_as(DP)
+
+
+def emu_fft(lib, x, nthr=96, f32=0):
+    T, D = x.shape
+    Tld = (T + 15) // 16 * 16
+    ser = np.zeros((D, Tld))
+    ser[:, :T] = x.T
+    row, part = np.zeros(Tld), np.zeros(Tld)
+    assert lib.emu_fft_acf(_p(ser), T, D, Tld, nthr, f32, _p(row), _p(part)) == 0
+    assert np.array_equal(row, part)
+    assert np.all(row[T:] == 0)
+    return row[:T]
+
+
+def emu_win(lib, x, mode, nwarps=4, f32=0):
+    T, D = x.shape
+    Tld = (T + 15) // 16 * 16
+    ser = np.zeros((D, Tld))
+    ser[:, :T] = x.T
+    res = np.zeros(T)
+    assert lib.emu_windowed(_p(ser), T, D, Tld, mode, nwarps, f32, _p(res)) == 0
+    return res
+
+
+@pytest.mark.parametrize("T", [1, 2, 3, 5, 10, 16, 17, 31, 33, 99, 100, 129, 250, 1000, 2047, 5001])
+def test_fft_phases_match_tidynamics_restatement(emu, T):
+    rng = np.random.default_rng(T)
+    for D in (1, 2, 3):
+        x = rng.standard_normal((T, D))
+        assert_close_normwise(emu_fft(emu, x), oracle.tidynamics_acf(x), 1e-11, f"T={T} D={D}")
+
+
+def test_fft_phases_thread_count_independent(emu):
+    x = np.random.default_rng(0).standard_normal((777, 3))
+    a = emu_fft(emu, x, nthr=32)
+    b = emu_fft(emu, x, nthr=640)
+    assert np.array_equal(a, b)
+
+
+def test_fft_plan_covers_input_and_uses_supported_radices(emu):
+    for T in list(range(1, 300)) + [4097, 5000, 5001, 8192, 10000, 16384]:
+        H, npz = ctypes.c_int(), ctypes.c_int()
+        rad = (ctypes.c_int * 12)()
+        assert emu.emu_plan(T, ctypes.byref(H), ctypes.byref(npz), rad) == 0
+        r = list(rad)[: npz.value]
+        assert H.value >= (T + 1) // 2 and int(np.prod(r)) == H.value
+        assert set(r) <= {2, 3, 4, 5, 8}
+
+
+@pytest.mark.parametrize("T", [1, 2, 15, 16, 17, 47, 48, 49, 100, 333, 1000])
+def test_windowed_phases(emu, T):
+    rng = np.random.default_rng(100 + T)
+    x = rng.standard_normal((T, 3)) * 3 + 1
+    prod = np.array([np.sum(x[: T - k] * x[k:]) for k in range(T)])
+    sq = np.array([np.sum((x[: T - k] - x[k:]) ** 2) for k in range(T)])
+    for nwarps in (1, 5):
+        assert_close_normwise(emu_win(emu, x, 0, nwarps), prod, 1e-13, "product")
+        got = emu_win(emu, x, 1, nwarps)
+        assert got[0] == 0.0
+        np.testing.assert_allclose(got, sq, rtol=1e-13, atol=0)
+
+
+def test_fp32_mode_tolerance(emu):
+    x = np.random.default_rng(5).standard_normal((2000, 3))
+    assert_close_normwise(emu_fft(emu, x, f32=1), oracle.tidynamics_acf(x), 1e-5, "fp32 fft")
+    prod = np.array([np.sum(x[: 2000 - k] * x[k:]) for k in range(2000)])
+    assert_close_normwise(emu_win(emu, x, 0, f32=1), prod, 1e-5, "fp32 windowed")

@@ -1,0 +1,267 @@
+"""Parity of the CUDA path against the oracle, through the public classes and
+the C ABI (ctypes).  FP64 bar: |gpu - ref| <= 1e-10 (|ref| + max|ref|) for the
+VACF routes (SURVEY.md section 7 tolerance definition; BASELINE.json states
+rel. 1e-10), plain rtol 1e-10 for Helfand; FP32 mode: 1e-5 on the same norm.
+"""
+import numpy as np
+import pytest
+from numpy.testing import assert_allclose, assert_almost_equal, assert_approx_equal
+
+import oracle
+from oracle.known_answers import ramp_trajectory
+from _util import assert_close_normwise
+from transport_analysis_b200 import _lib
+from transport_analysis_b200.synthetic import make_universe, random_trajectory
+from transport_analysis_b200.velocityautocorr import VelocityAutocorr as VACF
+from transport_analysis_b200.viscosity import ViscosityHelfand as VH
+
+pytestmark = pytest.mark.gpu
+
+DIMS = [("xyz", 3), ("xy", 2), ("xz", 2), ("yz", 2), ("x", 1), ("y", 1), ("z", 1)]
+TOL64 = 1e-10
+TOL32 = 1e-5
+BOX = [20.0, 21.0, 19.0, 90.0, 90.0, 90.0]
+
+
+def _f64(a):
+    return np.asarray(a, dtype=np.float64)
+
+
+@pytest.fixture(scope="module")
+def rand_u():
+    vel, pos = random_trajectory(700, 37, seed=11, with_positions=True, rho=0.9)
+    masses = np.random.default_rng(0).choice([1.008, 12.011, 15.999], 37)
+    return make_universe(pos, vel, masses=masses, dimensions=BOX), vel, pos, masses
+
+
+@pytest.fixture(scope="module")
+def step_u():
+    # the reference's step trajectory: v = t, x = t^2/2, mass 16, volume 8
+    t = np.arange(5001, dtype=np.float64)
+    v = np.repeat(t[:, None, None], 3, axis=2)
+    x = np.repeat((t * t / 2)[:, None, None], 3, axis=2)
+    return make_universe(x, v, masses=[16.0], dimensions=[2, 2, 2, 90, 90, 90])
+
+
+# ------------------------------------------------------------------ VACF
+@pytest.mark.parametrize("dim,n_dim", DIMS)
+@pytest.mark.parametrize("fft", [True, False])
+def test_vacf_random_all_dims(rand_u, dim, n_dim, fft):
+    u, vel, _, _ = rand_u
+    cols, _ = oracle.parse_dim_type(dim)
+    ref_bp, ref_ts = (oracle.vacf_fft if fft else oracle.vacf_windowed)(_f64(vel)[:, :, cols])
+    v = VACF(u.atoms, dim_type=dim, fft=fft).run()
+    assert v.results.timeseries.dtype == np.float64
+    assert v.results.vacf_by_particle.shape == (v.n_frames, v.n_particles)
+    assert_close_normwise(v.results.timeseries, ref_ts, TOL64, "timeseries")
+    assert_close_normwise(v.results.vacf_by_particle, ref_bp, TOL64, "by particle")
+
+
+@pytest.mark.parametrize("fft", [True, False])
+def test_vacf_sliced_subset_per_frame_path(rand_u, fft):
+    u, vel, _, _ = rand_u
+    ag = u.atoms[[3, 5, 6, 20, 36]]          # non-contiguous -> per-frame pinned-slab path
+    sl = slice(5, 690, 3)
+    ref_bp, ref_ts = (oracle.vacf_fft if fft else oracle.vacf_windowed)(_f64(vel)[sl][:, [3, 5, 6, 20, 36]])
+    v = VACF(ag, fft=fft).run(start=5, stop=690, step=3)
+    assert not v._stager.bulk_done
+    assert_close_normwise(v.results.timeseries, ref_ts, TOL64)
+    assert_close_normwise(v.results.vacf_by_particle, ref_bp, TOL64)
+    assert_allclose(v.times, np.arange(700.0)[sl])
+    # contiguous subset -> bulk path, same numbers as the per-frame path
+    ag2 = u.atoms[3:21]
+    vb = VACF(ag2, fft=fft).run(start=5, stop=690, step=3)
+    assert vb._stager.bulk_done
+    ref_bp, ref_ts = (oracle.vacf_fft if fft else oracle.vacf_windowed)(_f64(vel)[sl][:, 3:21])
+    assert_close_normwise(vb.results.timeseries, ref_ts, TOL64)
+
+
+@pytest.mark.parametrize("dim,n_dim", DIMS)
+def test_vacf_step_trajectory_known_answer(step_u, dim, n_dim):
+    # reference: TestAllDims (tests/test_velocityautocorr.py:331-360, :454-483)
+    poly = oracle.characteristic_poly(5001, n_dim)
+    v_fft = VACF(step_u.atoms, dim_type=dim, fft=True).run()
+    assert_almost_equal(v_fft.results.timeseries, poly, decimal=3)
+    if dim in ("xyz", "y"):
+        v_simple = VACF(step_u.atoms, dim_type=dim, fft=False).run()
+        assert_almost_equal(v_simple.results.timeseries, poly, decimal=4)
+        sd_expected = __import__("scipy").integrate.simpson(y=poly, x=range(5001)) / n_dim
+        assert_approx_equal(v_simple.self_diffusivity_gk(), sd_expected, significant=8)
+        assert_approx_equal(v_fft.self_diffusivity_gk(), sd_expected, significant=8)
+    poly = oracle.characteristic_poly(1000, n_dim, first=10, step=10)
+    for fft, dec in ((True, 3), (False, 4)):
+        v = VACF(step_u.atoms, dim_type=dim, fft=fft).run(start=10, stop=1000, step=10)
+        assert_almost_equal(v.results.timeseries, poly, decimal=dec)
+
+
+def test_notebook_vector_t10():
+    vel, _ = ramp_trajectory(10)
+    u = make_universe(None, vel)
+    assert_allclose(VACF(u.atoms, fft=True).run().results.timeseries, oracle.NOTEBOOK_VACF_T10_XYZ, atol=1e-11)
+    assert_allclose(VACF(u.atoms, fft=False).run().results.timeseries, oracle.NOTEBOOK_VACF_T10_XYZ, atol=1e-13)
+
+
+def test_against_reference_run(golden):
+    vel, pos = golden["rand_vel"], golden["rand_pos"]
+    u = make_universe(pos, vel, masses=golden["rand_masses"], dimensions=golden["rand_box"])
+    for dim, _ in DIMS:
+        v = VACF(u.atoms, dim_type=dim, fft=False).run()
+        assert_close_normwise(v.results.timeseries, golden[f"rand_vacf_windowed_{dim}_ts"], TOL64)
+        assert_close_normwise(v.results.vacf_by_particle, golden[f"rand_vacf_windowed_{dim}_bp"], TOL64)
+        v = VACF(u.atoms, dim_type=dim, fft=True).run()
+        assert_close_normwise(v.results.timeseries, golden[f"rand_vacf_fft_{dim}_ts"], TOL64)
+        assert_close_normwise(v.results.vacf_by_particle, golden[f"rand_vacf_fft_{dim}_bp"], TOL64)
+        h = VH(u.atoms, temp_avg=310.0, dim_type=dim).run()
+        assert_allclose(h.results.timeseries, golden[f"rand_helfand_{dim}_ts"], rtol=TOL64)
+        assert_allclose(h.results.visc_by_particle, golden[f"rand_helfand_{dim}_bp"], rtol=TOL64)
+    h = VH(u.atoms[1:5], linear_fit_window=(5, 30)).run(start=3, stop=150, step=4)
+    assert_allclose(h.results.timeseries, golden["rand_helfand_sliced_ts"], rtol=TOL64)
+    assert_allclose(h.results.viscosity, golden["rand_helfand_sliced_viscosity"], rtol=1e-9)
+    v = VACF(u.atoms, fft=False).run()
+    assert_allclose(v.self_diffusivity_gk(), golden["rand_gk"], rtol=1e-10)
+    assert_allclose(v.self_diffusivity_gk_odd(start=0, stop=159), golden["rand_gk_odd"], rtol=1e-10)
+    assert_allclose(v.self_diffusivity_gk(start=2, stop=100, step=3), golden["rand_gk_sliced"], rtol=1e-10)
+
+
+@pytest.mark.parametrize("T,N", [(1, 1), (2, 3), (3, 1), (15, 2), (16, 2), (17, 5), (33, 1), (257, 3), (1000, 300)])
+def test_edge_sizes(T, N):
+    vel, pos = random_trajectory(T, N, seed=T * 31 + N, with_positions=True)
+    u = make_universe(pos, vel, masses=np.linspace(1, 2, N), dimensions=BOX)
+    rw_bp, rw_ts = oracle.vacf_windowed(_f64(vel))
+    rf_bp, rf_ts = oracle.vacf_fft(_f64(vel))
+    assert_close_normwise(VACF(u.atoms, fft=False).run().results.vacf_by_particle, rw_bp, TOL64)
+    assert_close_normwise(VACF(u.atoms, fft=True).run().results.vacf_by_particle, rf_bp, TOL64)
+    vols = np.full(T, float(np.prod(np.float32(BOX[:3]).astype(np.float64))))
+    rh_bp, rh_ts = oracle.helfand_msd(_f64(vel), _f64(pos), np.linspace(1, 2, N), vols, 300.0)
+    h = VH(u.atoms).run()
+    assert_allclose(h.results.visc_by_particle, rh_bp, rtol=TOL64)
+    assert_allclose(h.results.timeseries, rh_ts, rtol=TOL64)
+
+
+# ------------------------------------------------------------------ Helfand
+@pytest.mark.parametrize("dim,n_dim", DIMS)
+def test_helfand_random_all_dims(rand_u, dim, n_dim):
+    u, vel, pos, masses = rand_u
+    cols, _ = oracle.parse_dim_type(dim)
+    vols = np.full(700, float(np.prod(np.float32(BOX[:3]).astype(np.float64))))
+    ref_bp, ref_ts = oracle.helfand_msd(_f64(vel)[:, :, cols], _f64(pos)[:, :, cols], masses, vols, 300.0)
+    h = VH(u.atoms, dim_type=dim).run()
+    assert h.results.timeseries[0] == 0.0 and np.all(h.results.visc_by_particle[0] == 0.0)
+    assert_allclose(h.results.timeseries, ref_ts, rtol=TOL64)
+    assert_allclose(h.results.visc_by_particle, ref_bp, rtol=TOL64)
+
+
+@pytest.mark.parametrize("dim,n_dim", [("xyz", 3), ("yz", 2), ("z", 1)])
+def test_helfand_step_trajectory_known_answer(step_u, dim, n_dim):
+    # reference: tests/test_viscosity.py:167-208 (assert_allclose, default rtol 1e-7)
+    cols, _ = oracle.parse_dim_type(dim)
+    vel, pos = ramp_trajectory(5001, 10, 10, 1000)
+    expect = oracle.characteristic_poly_helfand(vel[:, :, cols], pos[:, :, cols])
+    h = VH(step_u.atoms, dim_type=dim).run(start=10, stop=1000, step=10)
+    assert_allclose(h.results.timeseries, expect)
+    if dim == "xyz":
+        vel, pos = ramp_trajectory(5001)
+        expect = oracle.characteristic_poly_helfand(vel, pos)
+        assert_allclose(VH(step_u.atoms).run().results.timeseries, expect)
+
+
+def test_notebook_helfand_t10():
+    vel, pos = ramp_trajectory(10)
+    u = make_universe(pos, vel, masses=[16.0], dimensions=[2, 2, 2, 90, 90, 90])
+    assert_allclose(VH(u.atoms).run().results.timeseries * 3, oracle.NOTEBOOK_HELFAND_T10_SUMDIMS, rtol=1e-10)
+
+
+# ------------------------------------------------------------------ C ABI direct
+def test_c_abi_f64_source_lag_major_and_errors():
+    rng = np.random.default_rng(21)
+    T, N = 300, 9
+    vel = rng.standard_normal((T, N, 3))
+    ctx = _lib.Context([0])
+    with pytest.raises(_lib.BackendError, match="ta_stage_begin has not been called"):
+        ctx.T = T
+        ctx.vacf_fft()
+    ctx.stage_begin(T, N, [0, 2], np.float64, 1, None, "fp64")
+    with pytest.raises(_lib.BackendError, match="frames were staged"):
+        ctx.vacf_fft()
+    ctx.stage_bulk([vel])
+    ctx.stage_end()
+    ts = ctx.vacf_fft()
+    ref_bp, ref_ts = oracle.vacf_fft(vel[:, :, [0, 2]])
+    assert_close_normwise(ts, ref_ts, TOL64)
+    assert_close_normwise(ctx.fetch_by_particle(), ref_bp, TOL64)
+    lm = ctx.fetch_by_particle(lag_major_copy=True)
+    assert lm.flags.c_contiguous
+    assert np.array_equal(lm, ctx.fetch_by_particle())
+    assert np.array_equal(ctx.fetch_by_particle(2, 4), ctx.fetch_by_particle()[:, 2:6])
+    ts_w = ctx.vacf_windowed()            # same staged data, other route
+    assert_close_normwise(ts_w, oracle.vacf_windowed(vel[:, :, [0, 2]])[1], TOL64)
+    with pytest.raises(_lib.BackendError, match="n_fields == 2"):
+        ctx.helfand(np.ones(T), 1.0, 300.0)
+    assert ctx.launch_count() > 0
+    info = ctx.fft_plan_info()
+    assert info["H"] >= T // 2 and int(np.prod(info["radices"])) == info["H"]
+    ctx.close()
+
+
+def test_results_are_bit_reproducible(rand_u):
+    u = rand_u[0]
+    a = VACF(u.atoms).run().results.vacf_by_particle
+    b = VACF(u.atoms).run().results.vacf_by_particle
+    assert np.array_equal(a, b)
+
+
+def test_fp32_mode(rand_u):
+    u, vel, pos, masses = rand_u
+    for fft in (True, False):
+        ref_bp, ref_ts = (oracle.vacf_fft if fft else oracle.vacf_windowed)(_f64(vel))
+        v = VACF(u.atoms, fft=fft, precision="fp32").run()
+        assert_close_normwise(v.results.timeseries, ref_ts, TOL32)
+        assert_close_normwise(v.results.vacf_by_particle, ref_bp, TOL32)
+
+
+def test_lazy_by_particle(rand_u):
+    u = rand_u[0]
+    eager = VACF(u.atoms).run().results.vacf_by_particle
+    lazy = VACF(u.atoms, max_eager_bytes=0).run().results.vacf_by_particle
+    assert lazy.shape == eager.shape
+    assert np.array_equal(np.asarray(lazy), eager)
+    assert np.array_equal(lazy.particles(4, 9), eager[:, 4:9])
+
+
+# ------------------------------------------------------------------ size-independent properties at BASELINE sizes
+def test_properties_at_config_sizes():
+    """Config 1 size (1,000 x 5,000): the oracle is too slow for the full set,
+    so check (a) 16 sampled particles against the oracle, (b) lag 0 equals the
+    mean square, (c) the timeseries is the mean of the per-particle array,
+    (d) FFT route == windowed route, (e) acf(a x) = a^2 acf(x)."""
+    T, N = 5000, 1000
+    vel, _ = random_trajectory(T, N, seed=5)
+    u = make_universe(None, vel)
+    v = VACF(u.atoms, fft=True).run()
+    bp, ts = v.results.vacf_by_particle, v.results.timeseries
+    pick = np.random.default_rng(0).choice(N, 16, replace=False)
+    ref_bp, _ = oracle.vacf_fft(_f64(vel)[:, pick])
+    assert_close_normwise(bp[:, pick], ref_bp, TOL64)
+    assert_allclose(bp[0], (_f64(vel) ** 2).sum(axis=2).mean(axis=0), rtol=1e-12)
+    assert_allclose(ts, bp.mean(axis=1), rtol=1e-12, atol=1e-13 * np.abs(ts).max())
+    w = VACF(u.atoms[:64], fft=False).run()
+    assert_close_normwise(w.results.vacf_by_particle, bp[:, :64], TOL64)
+    u2 = make_universe(None, vel * np.float32(2.0))
+    v2 = VACF(u2.atoms[:256], fft=True).run()
+    assert_allclose(v2.results.vacf_by_particle, 4.0 * bp[:, :256], rtol=1e-12, atol=1e-12 * np.abs(bp).max())
+
+
+def test_multi_gpu_sharding_matches_single():
+    n = _lib.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    vel, pos = random_trajectory(400, 101, seed=9, with_positions=True)
+    u = make_universe(pos, vel, masses=np.ones(101), dimensions=BOX)
+    one = VACF(u.atoms, devices=[0]).run()
+    two = VACF(u.atoms, devices=list(range(min(n, 4)))).run()
+    assert np.array_equal(one.results.vacf_by_particle, two.results.vacf_by_particle)
+    assert_allclose(one.results.timeseries, two.results.timeseries, rtol=1e-13, atol=1e-14)
+    h1 = VH(u.atoms, devices=[0]).run()
+    h2 = VH(u.atoms, devices=[0, 1]).run()
+    assert np.array_equal(h1.results.visc_by_particle, h2.results.visc_by_particle)
+    assert_allclose(h1.results.timeseries, h2.results.timeseries, rtol=1e-13)

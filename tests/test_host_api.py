@@ -1,0 +1,123 @@
+"""Host-side behaviour that needs no GPU: the C-ABI library loads and exports
+every symbol include/ta_b200.h declares; constructor / run() error behaviour
+matches the reference (tests/test_velocityautocorr.py:132-149,201-217;
+tests/test_viscosity.py:139-155); the AnalysisBase stand-in slices frames like
+MDAnalysis; the product path fails loudly without a device."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import transport_analysis_b200 as tab
+from transport_analysis_b200 import _compat, _lib
+from transport_analysis_b200.synthetic import make_universe, random_trajectory
+from transport_analysis_b200.velocityautocorr import VelocityAutocorr as VACF
+from transport_analysis_b200.viscosity import ViscosityHelfand as VH
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def u():
+    vel, pos = random_trajectory(12, 10, seed=1, with_positions=True)
+    return make_universe(pos, vel, masses=np.full(10, 15.999), dimensions=[20, 20, 20, 90, 90, 90])
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "ta_b200.h")).read()
+    declared = set(re.findall(r"\b(ta_[a-z0-9_]+)\s*\(", header))
+    declared.discard("ta_ctx")
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    lib = _lib.load_library()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.ta_version() >= 100
+
+
+def test_no_oracle_import_in_product():
+    pkg = os.path.join(ROOT, "transport_analysis_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_fails_loudly_without_gpu(u):
+    if _lib.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(tab.BackendError, match="no CPU fallback"):
+        VACF(u.atoms).run()
+    with pytest.raises(tab.BackendError, match="no CPU fallback"):
+        VH(u.atoms).run()
+
+
+def test_no_velocities():
+    _, pos = random_trajectory(5, 10, with_positions=True)
+    u_no_vels = make_universe(pos, None, masses=np.ones(10), dimensions=[2, 2, 2, 90, 90, 90])
+    with pytest.raises(_compat.NoDataError, match="VACF computation requires velocities"):
+        VACF(u_no_vels.atoms, fft=False).run()
+    with pytest.raises(_compat.NoDataError, match="Helfand viscosity computation requires"):
+        VH(u_no_vels.atoms).run()
+
+
+def test_no_box_volume():
+    vel, pos = random_trajectory(5, 4, with_positions=True)
+    u_nobox = make_universe(pos, vel, masses=np.ones(4))
+    with pytest.raises(_compat.NoDataError, match="Helfand viscosity computation requires"):
+        VH(u_nobox.atoms).run()
+
+
+def test_updating_ag_rejected(u):
+    if _compat.HAVE_MDANALYSIS:
+        pytest.skip("needs the stand-in universe")
+    upd = u.select_atoms_updating([0, 1, 2])
+    with pytest.raises(TypeError, match="UpdatingAtomGroups are not valid"):
+        VACF(upd, fft=False)
+    with pytest.raises(TypeError, match="UpdatingAtomGroups are not valid"):
+        VH(upd)
+
+
+@pytest.mark.parametrize("dimtype", ["foo", "bar", "yx", "zyx"])
+def test_dimtype_error(u, dimtype):
+    with pytest.raises(ValueError, match=f"invalid dim_type: {dimtype}"):
+        VACF(u.atoms, dim_type=dimtype)
+    with pytest.raises(ValueError, match=f"invalid dim_type: {dimtype}"):
+        VH(u.atoms, dim_type=dimtype)
+
+
+def test_dimtype_case_insensitive(u):
+    v = VACF(u.atoms, dim_type="XZ")
+    assert v.dim_type == "xz" and v._dim == [0, 2] and v.dim_fac == 2
+
+
+def test_helpers_before_run(u):
+    v = VACF(u.atoms, fft=False)
+    for fn in (v.plot_vacf, v.self_diffusivity_gk, v.self_diffusivity_gk_odd, v.plot_running_integral):
+        with pytest.raises(RuntimeError, match="Analysis must be run"):
+            fn()
+
+
+@pytest.mark.skipif(_compat.HAVE_MDANALYSIS, reason="tests the stand-in driver")
+def test_standin_frame_slicing_matches_range():
+    vel, _ = random_trajectory(50, 2)
+    uu = make_universe(None, vel)
+
+    class Probe(_compat.AnalysisBase):
+        def __init__(self, traj):
+            super().__init__(traj)
+
+        def _prepare(self):
+            self.seen = []
+
+        def _single_frame(self):
+            self.seen.append((self._frame_index, self._ts.frame))
+
+    for sl in [(None, None, None), (10, 40, 7), (3, None, 2), (None, 20, None), (-10, None, 3)]:
+        p = Probe(uu.trajectory).run(*sl)
+        expect = list(range(50))[slice(*sl)]
+        assert [f for _, f in p.seen] == expect
+        assert p.n_frames == len(expect)
+        assert list(p.frames) == expect
+        np.testing.assert_array_equal(p.times, np.array(expect, dtype=float))

@@ -1,0 +1,261 @@
+"""ctypes binding of ``libta_b200.so`` (C ABI: ``include/ta_b200.h``).
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device
+is present, constructing a :class:`Context` raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_uint64, c_void_p
+
+import numpy as np
+
+TA_DTYPE_F32, TA_DTYPE_F64 = 0, 1
+TA_PRECISION_FP64, TA_PRECISION_FP32 = 0, 1
+TA_LAYOUT_ATOM_MAJOR, TA_LAYOUT_LAG_MAJOR = 0, 1
+TA_NCCL_ID_BYTES = 128
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libta_b200.so")
+
+# every symbol include/ta_b200.h declares: (restype, argtypes)
+_SIGNATURES = {
+    "ta_version": (c_int, []),
+    "ta_device_count": (c_int, [POINTER(c_int)]),
+    "ta_last_error": (c_char_p, [c_void_p]),
+    "ta_ctx_create": (c_int, [c_int, POINTER(c_int), POINTER(c_void_p)]),
+    "ta_nccl_unique_id": (c_int, [c_void_p]),
+    "ta_ctx_create_rank": (c_int, [c_int, c_int, c_int, c_void_p, POINTER(c_void_p)]),
+    "ta_ctx_destroy": (None, [c_void_p]),
+    "ta_host_register": (c_int, [c_void_p, c_uint64]),
+    "ta_host_unregister": (c_int, [c_void_p]),
+    "ta_stage_begin": (c_int, [c_void_p, c_int64, c_int64, c_int, POINTER(c_int), c_int, c_int,
+                               POINTER(c_double), c_int]),
+    "ta_stage_slot": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int64)]),
+    "ta_stage_commit": (c_int, [c_void_p, c_int64, c_int64]),
+    "ta_stage_bulk": (c_int, [c_void_p, POINTER(c_void_p), c_int64, c_int64, c_int64, c_int64, c_int64]),
+    "ta_stage_end": (c_int, [c_void_p]),
+    "ta_vacf_fft": (c_int, [c_void_p, POINTER(c_double)]),
+    "ta_vacf_windowed": (c_int, [c_void_p, POINTER(c_double)]),
+    "ta_helfand": (c_int, [c_void_p, POINTER(c_double), c_double, c_double, POINTER(c_double)]),
+    "ta_fetch_by_particle": (c_int, [c_void_p, c_int64, c_int64, c_int, POINTER(c_double)]),
+    "ta_timer_begin": (c_int, [c_void_p]),
+    "ta_timer_end": (c_int, [c_void_p, POINTER(c_float)]),
+    "ta_launch_count": (c_int64, [c_void_p]),
+    "ta_fft_plan_info": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int),
+                                 POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+class BackendError(RuntimeError):
+    """A libta_b200 call failed (the message carries ta_last_error())."""
+
+
+def load_library(path: str | None = None) -> ctypes.CDLL:
+    """Load libta_b200.so and declare its prototypes.  Raises if it is missing
+    (build it with ``python -c 'import __graft_entry__ as g; g.build()'``)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise BackendError(
+            f"{path} not found: the CUDA backend has not been built "
+            "(run __graft_entry__.build()); there is no CPU fallback"
+        )
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def device_count() -> int:
+    n = c_int(0)
+    load_library().ta_device_count(ctypes.byref(n))
+    return n.value
+
+
+def nccl_unique_id() -> bytes:
+    lib = load_library()
+    buf = ctypes.create_string_buffer(TA_NCCL_ID_BYTES)
+    rc = lib.ta_nccl_unique_id(buf)
+    if rc != 0:
+        raise BackendError(f"ta_nccl_unique_id failed ({rc}): {lib.ta_last_error(None).decode()}")
+    return buf.raw
+
+
+def _dptr(a: np.ndarray):
+    return a.ctypes.data_as(POINTER(c_double))
+
+
+class Context:
+    """One analysis context = one ``ta_ctx`` (device memory, streams, NCCL)."""
+
+    def __init__(self, devices=None, rank: int | None = None, nranks: int = 1, nccl_id: bytes | None = None):
+        self._lib = load_library()
+        self._h = c_void_p()
+        if rank is not None:
+            dev = 0 if devices is None else int(devices[0] if np.ndim(devices) else devices)
+            idbuf = ctypes.create_string_buffer(nccl_id, TA_NCCL_ID_BYTES) if nccl_id else None
+            rc = self._lib.ta_ctx_create_rank(dev, int(rank), int(nranks), idbuf, ctypes.byref(self._h))
+        else:
+            if devices is None:
+                devices = [0]
+            devs = (c_int * len(devices))(*[int(d) for d in devices])
+            rc = self._lib.ta_ctx_create(len(devices), devs, ctypes.byref(self._h))
+        if rc != 0:
+            msg = self._lib.ta_last_error(None).decode()
+            self._h = c_void_p()
+            raise BackendError(f"cannot create a B200 context ({rc}): {msg}")
+        self.T = self.N = 0
+        self._n_fields = 1
+        self._np_dtype = np.float32
+
+    # -- plumbing ---------------------------------------------------------
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise BackendError(f"{what} failed ({rc}): {self._lib.ta_last_error(self._h).decode()}")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.ta_ctx_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- staging ----------------------------------------------------------
+    def stage_begin(self, T, N, dims, src_dtype=np.float32, n_fields=1, masses=None, precision="fp64"):
+        dims = [int(d) for d in dims]
+        cd = (c_int * len(dims))(*dims)
+        np_dtype = np.dtype(src_dtype)
+        if np_dtype == np.float32:
+            code = TA_DTYPE_F32
+        elif np_dtype == np.float64:
+            code = TA_DTYPE_F64
+        else:
+            raise ValueError(f"unsupported source dtype {np_dtype}")
+        prec = {"fp64": TA_PRECISION_FP64, "fp32": TA_PRECISION_FP32}[precision]
+        mptr = None
+        if masses is not None:
+            self._masses = np.ascontiguousarray(masses, dtype=np.float64)
+            mptr = _dptr(self._masses)
+        self._check(
+            self._lib.ta_stage_begin(self._h, int(T), int(N), len(dims), cd, code, int(n_fields), mptr, prec),
+            "ta_stage_begin",
+        )
+        self.T, self.N, self._n_fields, self._np_dtype = int(T), int(N), int(n_fields), np_dtype
+
+    def stage_slot(self) -> np.ndarray:
+        """Pinned slab as an array [capacity, n_fields, N, 3] of the source dtype."""
+        ptr, cap = c_void_p(), c_int64()
+        self._check(self._lib.ta_stage_slot(self._h, ctypes.byref(ptr), ctypes.byref(cap)), "ta_stage_slot")
+        shape = (cap.value, self._n_fields, self.N, 3)
+        nbytes = int(np.prod(shape)) * self._np_dtype.itemsize
+        buf = (ctypes.c_char * nbytes).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=self._np_dtype).reshape(shape)
+
+    def stage_commit(self, frame0: int, nframes: int):
+        self._check(self._lib.ta_stage_commit(self._h, int(frame0), int(nframes)), "ta_stage_commit")
+
+    def stage_bulk(self, fields, atom_first=0, frame_first=0, frame_step=1, nframes=None):
+        """fields: list of C-contiguous [F, A, 3] arrays of the source dtype."""
+        arrs = []
+        for a in fields:
+            if a.dtype != self._np_dtype or not a.flags.c_contiguous or a.ndim != 3 or a.shape[2] != 3:
+                raise ValueError("bulk fields must be C-contiguous [frames, atoms, 3] arrays of the staged dtype")
+            arrs.append(a)
+        src_atoms = arrs[0].shape[1]
+        nframes = self.T if nframes is None else nframes
+        last = frame_first + (nframes - 1) * frame_step
+        if last >= arrs[0].shape[0]:
+            raise ValueError("frame window exceeds the source array")
+        ptrs = (c_void_p * 2)(*([a.ctypes.data for a in arrs] + [None] * (2 - len(arrs))))
+        self._keepalive = arrs
+        self._check(
+            self._lib.ta_stage_bulk(self._h, ptrs, int(src_atoms), int(atom_first), int(frame_first),
+                                    int(frame_step), int(nframes)),
+            "ta_stage_bulk",
+        )
+
+    def stage_end(self):
+        self._check(self._lib.ta_stage_end(self._h), "ta_stage_end")
+        self._keepalive = None
+
+    # -- compute ----------------------------------------------------------
+    def vacf_fft(self) -> np.ndarray:
+        ts = np.empty(self.T, dtype=np.float64)
+        self._check(self._lib.ta_vacf_fft(self._h, _dptr(ts)), "ta_vacf_fft")
+        return ts
+
+    def vacf_windowed(self) -> np.ndarray:
+        ts = np.empty(self.T, dtype=np.float64)
+        self._check(self._lib.ta_vacf_windowed(self._h, _dptr(ts)), "ta_vacf_windowed")
+        return ts
+
+    def helfand(self, volumes, boltzmann: float, temp_avg: float) -> np.ndarray:
+        vol = np.ascontiguousarray(volumes, dtype=np.float64)
+        if vol.shape != (self.T,):
+            raise ValueError("volumes must have one entry per analysed frame")
+        ts = np.empty(self.T, dtype=np.float64)
+        self._check(self._lib.ta_helfand(self._h, _dptr(vol), float(boltzmann), float(temp_avg), _dptr(ts)),
+                    "ta_helfand")
+        return ts
+
+    def fetch_by_particle(self, atom0=0, natoms=None, lag_major_copy=False) -> np.ndarray:
+        """Per-particle results as an array of shape (T, natoms), the reference's
+        shape (velocityautocorr.py:145-147).  By default it is a transposed view
+        of the atom-major device buffer (no extra pass); ``lag_major_copy=True``
+        has the device produce the C-contiguous lag-major layout."""
+        natoms = self.N - atom0 if natoms is None else natoms
+        if lag_major_copy:
+            out = np.empty((self.T, natoms), dtype=np.float64)
+            self._check(self._lib.ta_fetch_by_particle(self._h, int(atom0), int(natoms), TA_LAYOUT_LAG_MAJOR,
+                                                       _dptr(out)), "ta_fetch_by_particle")
+            return out
+        out = np.empty((natoms, self.T), dtype=np.float64)
+        self._check(self._lib.ta_fetch_by_particle(self._h, int(atom0), int(natoms), TA_LAYOUT_ATOM_MAJOR,
+                                                   _dptr(out)), "ta_fetch_by_particle")
+        return out.T
+
+    # -- timing / introspection -------------------------------------------
+    def timer_begin(self):
+        self._check(self._lib.ta_timer_begin(self._h), "ta_timer_begin")
+
+    def timer_end(self) -> float:
+        ms = c_float()
+        self._check(self._lib.ta_timer_end(self._h, ctypes.byref(ms)), "ta_timer_end")
+        return float(ms.value)
+
+    def launch_count(self) -> int:
+        return int(self._lib.ta_launch_count(self._h))
+
+    def fft_plan_info(self) -> dict:
+        H, npz, thr, smem, grid = c_int(), c_int(), c_int(), c_int(), c_int()
+        rad = (c_int * 12)()
+        self._lib.ta_fft_plan_info(self._h, ctypes.byref(H), ctypes.byref(npz), rad, ctypes.byref(thr),
+                                   ctypes.byref(smem), ctypes.byref(grid))
+        return {"H": H.value, "radices": list(rad)[: npz.value], "threads": thr.value,
+                "smem_bytes": smem.value, "grid": grid.value}
+
+
+def host_register(arr: np.ndarray):
+    lib = load_library()
+    rc = lib.ta_host_register(c_void_p(arr.ctypes.data), c_uint64(arr.nbytes))
+    if rc != 0:
+        raise BackendError(f"ta_host_register failed ({rc}): {lib.ta_last_error(None).decode()}")
+
+
+def host_unregister(arr: np.ndarray):
+    lib = load_library()
+    lib.ta_host_unregister(c_void_p(arr.ctypes.data))

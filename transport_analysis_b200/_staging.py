@@ -1,0 +1,138 @@
+"""Host side of `_single_frame` staging, shared by both analysis classes.
+
+The reference copies one frame at a time into a host ``[T, N, D]`` float64
+array (velocityautocorr.py:150-152,192-194; viscosity.py:128-134,189-199).
+Here frames are batched into pinned slabs owned by the backend and streamed
+to HBM with asynchronous copies that overlap the trajectory loop; when the
+reader already holds the whole trajectory in memory (MemoryReader) the
+per-frame loop is bypassed and the array is streamed directly.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from . import _lib
+
+
+def resolve_devices(devices):
+    if devices is None:
+        env = os.environ.get("TA_B200_DEVICES")
+        if env:
+            return [int(x) for x in env.split(",") if x.strip() != ""]
+        return [0]
+    if isinstance(devices, (int, np.integer)):
+        return [int(devices)]
+    return [int(d) for d in devices]
+
+
+class LazyByParticle:
+    """Array-like handle on a per-particle result that is still on the GPUs.
+
+    ``np.asarray(handle)`` or ``handle[...]`` materialises it with the
+    reference's shape ``(n_frames, n_particles)``; ``handle.particles(a, b)``
+    fetches only particles a..b-1.
+    """
+
+    def __init__(self, ctx: "_lib.Context", T: int, N: int):
+        self._ctx, self.shape, self.dtype, self.ndim = ctx, (T, N), np.dtype(np.float64), 2
+        self._cache = None
+
+    def particles(self, start: int, stop: int) -> np.ndarray:
+        return self._ctx.fetch_by_particle(start, stop - start)
+
+    def __array__(self, dtype=None, copy=None):
+        if self._cache is None:
+            self._cache = self._ctx.fetch_by_particle(0, self.shape[1])
+        return self._cache if dtype is None else self._cache.astype(dtype)
+
+    def __getitem__(self, item):
+        return np.asarray(self)[item]
+
+    def __len__(self):
+        return self.shape[0]
+
+
+class FrameStager:
+    """Drives ta_stage_begin / slot / commit / bulk for one ``run()``."""
+
+    def __init__(self, devices, n_frames: int, n_particles: int, dim_cols, n_fields: int,
+                 masses, precision: str):
+        self._devices = devices
+        self._ctx = None
+        self.T, self.N = int(n_frames), int(n_particles)
+        self.dim_cols, self.n_fields = list(dim_cols), n_fields
+        self.masses, self.precision = masses, precision
+        self._begun = False
+        self._slab = None
+        self._slab_frame0 = 0
+        self._fill = 0
+        self.bulk_done = False
+
+    @property
+    def ctx(self) -> "_lib.Context":
+        """The backend context, created on first use (so that data-presence
+        errors surface before any device work, as in the reference); raises
+        BackendError if the CUDA library or a GPU is missing."""
+        if self._ctx is None:
+            self._ctx = _lib.Context(self._devices)
+        return self._ctx
+
+    # -- whole-trajectory fast path ------------------------------------------
+    def try_bulk(self, reader, atom_ix, start, stop, step, need_positions: bool) -> bool:
+        """Stream straight from an in-memory reader.  Conditions: 'fac' ordered
+        float32 arrays, a regular frame slice with step >= 1 and a contiguous
+        run of atoms; otherwise the per-frame path is used."""
+        if start is None or step is None or step < 1:
+            return False
+        if getattr(reader, "stored_order", None) != "fac":
+            return False
+        vel = getattr(reader, "velocity_array", None)
+        if vel is None:
+            return False
+        fields = [vel]
+        if need_positions:
+            pos = reader.get_array() if hasattr(reader, "get_array") else getattr(reader, "coordinate_array", None)
+            if pos is None:
+                return False
+            fields.append(pos)
+        for a in fields:
+            if not isinstance(a, np.ndarray) or a.dtype != np.float32 or a.ndim != 3 or not a.flags.c_contiguous:
+                return False
+        ix = np.asarray(atom_ix)
+        if len(ix) == 0 or not np.array_equal(ix, np.arange(ix[0], ix[0] + len(ix))):
+            return False
+        self.ctx.stage_begin(self.T, self.N, self.dim_cols, np.float32, self.n_fields, self.masses, self.precision)
+        self._begun = True
+        self.ctx.stage_bulk(fields, atom_first=int(ix[0]), frame_first=int(start), frame_step=int(step),
+                            nframes=self.T)
+        self.bulk_done = True
+        return True
+
+    # -- per-frame path ----------------------------------------------------
+    def add_frame(self, frame_index: int, velocities: np.ndarray, positions=None):
+        if not self._begun:
+            dtype = np.float32 if velocities.dtype == np.float32 else np.float64
+            self.ctx.stage_begin(self.T, self.N, self.dim_cols, dtype, self.n_fields, self.masses, self.precision)
+            self._begun = True
+        if self._slab is None:
+            self._slab = self.ctx.stage_slot()
+            self._slab_frame0 = frame_index
+            self._fill = 0
+        self._slab[self._fill, 0] = velocities
+        if self.n_fields == 2:
+            self._slab[self._fill, 1] = positions
+        self._fill += 1
+        if self._fill == self._slab.shape[0]:
+            self.flush()
+
+    def flush(self):
+        if self._slab is not None and self._fill > 0:
+            self.ctx.stage_commit(self._slab_frame0, self._fill)
+        self._slab = None
+        self._fill = 0
+
+    def finish(self):
+        self.flush()
+        self.ctx.stage_end()

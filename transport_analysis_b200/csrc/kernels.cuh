@@ -1,0 +1,230 @@
+// sm_100a kernels of the time-correlation hot path.  The per-CTA arithmetic
+// lives in fft_core.cuh / windowed_core.cuh; this file wraps it in persistent
+// CTAs (one particle at a time, static round-robin so results are
+// bit-reproducible run to run) and adds the staging transposition and the
+// small reduction / layout kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include "ta_common.cuh"
+#include "fft_core.cuh"
+#include "windowed_core.cuh"
+
+namespace ta {
+
+// ---------------------------------------------------------------------------
+// K0: staging transposition.  Frame-major slab [nframes][natoms][3] (f32 or
+// f64, as copied from the host) -> atom-major, time-contiguous series
+// [natoms][D][Tld] f64 at frame offset frame0, selecting the dim_type columns.
+// Replaces the per-frame copies of VelocityAutocorr._single_frame
+// (velocityautocorr.py:192-194) and ViscosityHelfand._single_frame
+// (viscosity.py:189-199); with HELFAND it also forms g = (m*v)*x, the product
+// viscosity.py:213-218 evaluates per lag (same association, so bit-identical).
+// ---------------------------------------------------------------------------
+constexpr int K0_FR = 32;   // frames per tile
+constexpr int K0_AT = 32;   // atoms per tile
+
+template <typename SRC, bool HELFAND>
+__global__ void __launch_bounds__(256)
+k0_stage(const SRC* __restrict__ v, const SRC* __restrict__ x, const double* __restrict__ masses,
+         double* __restrict__ series, int natoms, int nframes, long long frame0, long long Tld,
+         int D, int d0, int d1, int d2) {
+    __shared__ double tile[K0_FR][K0_AT * 3 + 1];
+    const int a0 = blockIdx.x * K0_AT;
+    const int f0 = blockIdx.y * K0_FR;
+    const int na = min(K0_AT, natoms - a0);
+    const int nf = min(K0_FR, nframes - f0);
+    const int ncol = na * 3;
+    for (int f = threadIdx.y; f < nf; f += blockDim.y) {
+        const size_t rowoff = ((size_t)(f0 + f) * natoms + a0) * 3;
+        for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
+            double val = (double)v[rowoff + c];
+            if (HELFAND) {
+                double m = masses[a0 + c / 3];
+                val = (m * val) * (double)x[rowoff + c];
+            }
+            tile[f][c] = val;
+        }
+    }
+    __syncthreads();
+    const int dims[3] = {d0, d1, d2};
+    const int nrows = na * D;
+    for (int r = threadIdx.y; r < nrows; r += blockDim.y) {
+        const int a = r / D, d = r - a * D;
+        double* dst = series + ((size_t)(a0 + a) * D + d) * Tld + frame0 + f0;
+        const int col = a * 3 + dims[d];
+        for (int f = threadIdx.x; f < nf; f += blockDim.x) dst[f] = tile[f][col];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K1: FFT autocorrelation, one particle per CTA iteration.
+// ---------------------------------------------------------------------------
+template <typename R>
+struct K1Args {
+    FftTables<R> t;              // tw_lo / tw_hi point to GLOBAL copies here
+    int nlo, nhi;
+    const double* series;        // [natoms][D][Tld]
+    double* by_particle;         // [natoms][Tld]
+    double* partial;             // [gridDim.x][Tld]
+    int natoms, D;
+    long long Tld;
+};
+
+constexpr int K1_MAX_THREADS = 640;
+
+template <typename R>
+__global__ void __launch_bounds__(K1_MAX_THREADS)
+k1_fft_acf(const K1Args<R> args) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int H = args.t.H;
+    cplx<R>* buf = reinterpret_cast<cplx<R>*>(smem_raw);
+    cplx<R>* tw_lo = buf + H;
+    cplx<R>* tw_hi = tw_lo + args.nlo;
+    R* sd = reinterpret_cast<R*>(tw_hi + args.nhi);
+
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    FftTables<R> t = args.t;
+    for (int i = tid; i < args.nlo; i += nthr) tw_lo[i] = args.t.tw_lo[i];
+    for (int i = tid; i < args.nhi; i += nthr) tw_hi[i] = args.t.tw_hi[i];
+    t.tw_lo = tw_lo;
+    t.tw_hi = tw_hi;
+    __syncthreads();
+
+    double* partial = args.partial + (size_t)blockIdx.x * args.Tld;
+    for (int a = blockIdx.x; a < args.natoms; a += gridDim.x) {
+        const double* ser = args.series + (size_t)a * args.D * args.Tld;
+        double* row = args.by_particle + (size_t)a * args.Tld;
+        for (int r = 0; r < 2; ++r) {
+            fft_zero_acc<R>(tid, nthr, sd, t);
+            for (int d = 0; d < args.D; ++d) {
+                fft_load<R>(tid, nthr, buf, ser + (size_t)d * args.Tld, t, r);
+                __syncthreads();
+                int size = H;
+                for (int ps = 0; ps < t.npasses; ++ps) {
+                    const int s = size / t.radix[ps];
+                    dif_pass_any<R>(t.radix[ps], tid, nthr, buf, t, s);
+                    __syncthreads();
+                    size = s;
+                }
+                fft_accumulate<R>(tid, nthr, buf, sd, t, r);
+                __syncthreads();
+            }
+            fft_build<R>(tid, nthr, buf, sd, t, r);
+            __syncthreads();
+            int s = 1;
+            for (int ps = t.npasses - 1; ps >= 0; --ps) {
+                dit_pass_any<R>(t.radix[ps], tid, nthr, buf, t, s);
+                __syncthreads();
+                s *= t.radix[ps];
+            }
+            fft_store<R>(tid, nthr, buf, row, partial, t, r);
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K2 / K3: windowed lag sums, one particle per CTA iteration.
+//   MODE = TA_WIN_PRODUCT: vacf[k]  = sum_d sum_i g_d[i] g_d[i+k] / (T-k)
+//   MODE = TA_WIN_SQDIFF : visc[k]  = sum_d sum_i (g_d[i]-g_d[i+k])^2 / (D (T-k)) / denom
+// ---------------------------------------------------------------------------
+struct WinArgs {
+    const double* series;   // [natoms][D][Tld]
+    double* by_particle;    // [natoms][Tld]
+    double* partial;        // [gridDim.x][Tld]
+    int natoms, D, T;
+    long long Tld;
+    double denom;           // Helfand: 2 kB <V> temp_avg ; VACF: unused
+};
+
+constexpr int KW_MAX_THREADS = 512;
+
+template <typename R, int MODE>
+__global__ void __launch_bounds__(KW_MAX_THREADS)
+k_windowed(const WinArgs args) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = args.T;
+    const int ne = win_smem_elems(T);
+    R* S = reinterpret_cast<R*>(smem_raw);
+    double* res = reinterpret_cast<double*>(S + ((ne + 1) & ~1));
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    const int nlb = win_num_lag_blocks(T), npairs = win_num_pairs(nlb);
+    double* partial = args.partial + (size_t)blockIdx.x * args.Tld;
+
+    for (int a = blockIdx.x; a < args.natoms; a += gridDim.x) {
+        for (int k = tid; k < T; k += nthr) res[k] = 0.0;
+        for (int d = 0; d < args.D; ++d) {
+            const double* ser = args.series + ((size_t)a * args.D + d) * args.Tld;
+            __syncthreads();   // previous series fully consumed
+            for (int x = tid; x < ne; x += nthr) S[x] = (R)0;
+            __syncthreads();
+            for (int x = tid; x < T; x += nthr) S[win_addr(x)] = (R)ser[x];
+            __syncthreads();
+            for (int pair = warp; pair < npairs; pair += nwarps) {
+                int kbs[2];
+                win_pair_blocks(pair, nlb, &kbs[0], &kbs[1]);
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    const int kb = kbs[h];
+                    if (kb < 0) continue;
+                    R acc[TA_WIN_LAGS];
+#pragma unroll
+                    for (int m = 0; m < TA_WIN_LAGS; ++m) acc[m] = (R)0;
+                    win_lane_accumulate<R, MODE>(lane, 32, S, T, kb, acc);
+                    double mine = 0.0;
+#pragma unroll
+                    for (int m = 0; m < TA_WIN_LAGS; ++m) {
+                        double v = (double)acc[m];
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                        if (lane == m) mine = v;
+                    }
+                    const int k = kb * TA_WIN_LAGS + lane;
+                    if (lane < TA_WIN_LAGS && k < T) res[k] += mine;   // lag k is owned by this warp only
+                }
+            }
+        }
+        __syncthreads();
+        double* row = args.by_particle + (size_t)a * args.Tld;
+        for (int k = tid; k < T; k += nthr) {
+            double val;
+            if (MODE == TA_WIN_PRODUCT) val = res[k] / (double)(T - k);
+            else val = res[k] / ((double)args.D * (double)(T - k)) / args.denom;
+            row[k] = val;
+            partial[k] += val;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K4a: fixed-order sum of the per-CTA partial rows -> atom sum of this shard.
+// ---------------------------------------------------------------------------
+__global__ void k_sum_partials(const double* __restrict__ partial, int nrows, long long Tld, int T,
+                               double* __restrict__ out) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= T) return;
+    double s = 0.0;
+    for (int r = 0; r < nrows; ++r) s += partial[(size_t)r * Tld + k];
+    out[k] = s;
+}
+
+// K4b: lag-major view of the per-particle result for a range of atoms:
+// out[k][j] = by_particle[atom0 + j][k]   (reference layout, velocityautocorr.py:145-147)
+__global__ void k_to_lag_major(const double* __restrict__ by_particle, long long Tld, int T,
+                               long long atom0, int natoms, double* __restrict__ out) {
+    __shared__ double tile[32][33];
+    const int k0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+    for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
+        int j = j0 + jj, k = k0 + threadIdx.x;
+        if (j < natoms && k < T) tile[jj][threadIdx.x] = by_particle[(size_t)(atom0 + j) * Tld + k];
+    }
+    __syncthreads();
+    for (int kk = threadIdx.y; kk < 32; kk += blockDim.y) {
+        int k = k0 + kk, j = j0 + threadIdx.x;
+        if (j < natoms && k < T) out[(size_t)k * natoms + j] = tile[threadIdx.x][kk];
+    }
+}
+
+}  // namespace ta

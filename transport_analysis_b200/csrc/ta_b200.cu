@@ -1,0 +1,826 @@
+// libta_b200.so -- host runtime + C ABI (include/ta_b200.h) around the sm_100a
+// kernels in kernels.cuh.  Plain CUDA runtime + NCCL (dlopen'ed, only touched
+// when more than one device / rank takes part); no PyTorch, no CPU fallback.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ta_b200.h"
+#include "fft_plan.h"
+#include "kernels.cuh"
+
+using namespace ta;
+
+namespace {
+
+std::string g_last_error;  // for failures before a context exists
+
+// ------------------------------------------------------------------ NCCL (lazy)
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+bool nccl_load(std::string* err) {
+    if (g_nccl.handle) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names) {
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) {
+        *err = std::string("cannot dlopen libnccl.so.2: ") + dlerror();
+        return false;
+    }
+#define TA_SYM(field, name)                                             \
+    g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(h, name)); \
+    if (!g_nccl.field) { *err = std::string("NCCL symbol missing: ") + name; return false; }
+    TA_SYM(GetUniqueId, "ncclGetUniqueId");
+    TA_SYM(CommInitRank, "ncclCommInitRank");
+    TA_SYM(CommInitAll, "ncclCommInitAll");
+    TA_SYM(CommDestroy, "ncclCommDestroy");
+    TA_SYM(AllReduce, "ncclAllReduce");
+    TA_SYM(GroupStart, "ncclGroupStart");
+    TA_SYM(GroupEnd, "ncclGroupEnd");
+    TA_SYM(GetErrorString, "ncclGetErrorString");
+#undef TA_SYM
+    g_nccl.handle = h;
+    return true;
+}
+
+constexpr int kNumSlabs = 3;
+constexpr int kNumDevStage = 2;
+
+struct Shard {
+    int dev = 0;
+    int num_sms = 0;
+    int max_smem = 0;
+    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    cudaEvent_t ev_copy_done[kNumDevStage] = {nullptr, nullptr};
+    cudaEvent_t ev_k0_done[kNumDevStage] = {nullptr, nullptr};
+    cudaEvent_t ev_slab[kNumSlabs] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    ncclComm_t comm = nullptr;
+    // problem-sized state
+    int64_t atom0 = 0, natoms = 0;
+    double natoms_d = 0.0;
+    double* series = nullptr;
+    double* by_particle = nullptr;
+    double* masses = nullptr;
+    double* ts_sum = nullptr;
+    double* partial = nullptr;
+    size_t partial_rows = 0;
+    void* dstage[kNumDevStage][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    int stage_toggle = 0;
+    double* lagmajor_tmp = nullptr;
+    size_t lagmajor_bytes = 0;
+    // FFT tables
+    void* tw_lo = nullptr;
+    void* tw_hi = nullptr;
+    uint32_t* ftab = nullptr;
+    uint32_t* pair0 = nullptr;
+    uint32_t* own0 = nullptr;
+};
+
+}  // namespace
+
+struct ta_ctx {
+    std::vector<Shard> sh;
+    int rank = 0, nranks = 1;
+    bool have_comm = false;
+    std::string err;
+    // problem
+    bool begun = false;
+    int64_t T = 0, N = 0, Tld = 0;
+    int D = 0, dims[3] = {0, 1, 2};
+    int src_dtype = TA_DTYPE_F32, n_fields = 1, precision = TA_PRECISION_FP64;
+    size_t elt = 4;
+    int64_t frames_staged = 0;
+    // pinned slab ring
+    void* slab[kNumSlabs] = {nullptr, nullptr, nullptr};
+    int64_t slab_frames = 0;
+    int cur_slab = -1;       // slab handed out by the last ta_stage_slot
+    int next_slab = 0;
+    bool slab_used[kNumSlabs] = {false, false, false};
+    // FFT plan cache
+    FftPlanHost plan;
+    int64_t plan_T = -1;
+    int plan_prec = -1;
+    int npairs0 = 0;
+    int k1_threads = 0, k1_smem = 0, k1_grid = 0;
+    std::vector<double> host_ts;
+    int64_t launches = 0;
+};
+
+namespace {
+
+int fail(ta_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    g_last_error = msg;
+    return code;
+}
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(ctx, TA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+#define CKN(call)                                                                         \
+    do {                                                                                  \
+        ncclResult_t r_ = (call);                                                         \
+        if (r_ != ncclSuccess)                                                            \
+            return fail(ctx, TA_ERR_NCCL, std::string(#call) + ": " + g_nccl.GetErrorString(r_)); \
+    } while (0)
+
+void free_problem(ta_ctx* c) {
+    for (auto& s : c->sh) {
+        cudaSetDevice(s.dev);
+        cudaStreamSynchronize(s.s_compute);
+        cudaStreamSynchronize(s.s_copy);
+        cudaFree(s.series); s.series = nullptr;
+        cudaFree(s.by_particle); s.by_particle = nullptr;
+        cudaFree(s.masses); s.masses = nullptr;
+        cudaFree(s.ts_sum); s.ts_sum = nullptr;
+        cudaFree(s.partial); s.partial = nullptr; s.partial_rows = 0;
+        cudaFree(s.lagmajor_tmp); s.lagmajor_tmp = nullptr; s.lagmajor_bytes = 0;
+        for (int b = 0; b < kNumDevStage; ++b)
+            for (int f = 0; f < 2; ++f) { cudaFree(s.dstage[b][f]); s.dstage[b][f] = nullptr; }
+        cudaFree(s.tw_lo); s.tw_lo = nullptr;
+        cudaFree(s.tw_hi); s.tw_hi = nullptr;
+        cudaFree(s.ftab); s.ftab = nullptr;
+        cudaFree(s.pair0); s.pair0 = nullptr;
+        cudaFree(s.own0); s.own0 = nullptr;
+    }
+    for (int i = 0; i < kNumSlabs; ++i) {
+        if (c->slab[i]) cudaFreeHost(c->slab[i]);
+        c->slab[i] = nullptr;
+        c->slab_used[i] = false;
+    }
+    c->begun = false;
+    c->plan_T = -1;
+    c->frames_staged = 0;
+    c->cur_slab = -1;
+    c->next_slab = 0;
+}
+
+int init_shard(ta_ctx* ctx, Shard& s, int dev) {
+    s.dev = dev;
+    CK(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10)
+        return fail(ctx, TA_ERR_UNSUPPORTED,
+                    std::string("device ") + prop.name + " is not sm_100 class; this library is built for sm_100a only");
+    s.num_sms = prop.multiProcessorCount;
+    CK(cudaDeviceGetAttribute(&s.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    CK(cudaStreamCreateWithFlags(&s.s_compute, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&s.s_copy, cudaStreamNonBlocking));
+    for (int b = 0; b < kNumDevStage; ++b) {
+        CK(cudaEventCreateWithFlags(&s.ev_copy_done[b], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s.ev_k0_done[b], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < kNumSlabs; ++i) CK(cudaEventCreateWithFlags(&s.ev_slab[i], cudaEventDisableTiming));
+    CK(cudaEventCreate(&s.ev_t0));
+    CK(cudaEventCreate(&s.ev_t1));
+    return TA_OK;
+}
+
+int sync_all(ta_ctx* ctx) {
+    for (auto& s : ctx->sh) {
+        CK(cudaSetDevice(s.dev));
+        CK(cudaStreamSynchronize(s.s_copy));
+        CK(cudaStreamSynchronize(s.s_compute));
+    }
+    return TA_OK;
+}
+
+// Enqueue H2D of `nframes` frames for every shard + the K0 transposition.
+// `base[f]`: host pointer to (frame 0 of this chunk, source atom 0 of particle
+// 0) of field f; consecutive analysed frames are `pitch` bytes apart.
+int enqueue_chunk(ta_ctx* ctx, const char* const* base, size_t pitch, int64_t frame0, int64_t nframes,
+                  int slab_index) {
+    const size_t elt = ctx->elt;
+    for (auto& s : ctx->sh) {
+        if (s.natoms == 0) continue;
+        CK(cudaSetDevice(s.dev));
+        const int b = s.stage_toggle;
+        s.stage_toggle ^= 1;
+        CK(cudaStreamWaitEvent(s.s_copy, s.ev_k0_done[b], 0));
+        const size_t width = (size_t)s.natoms * 3 * elt;
+        for (int f = 0; f < ctx->n_fields; ++f) {
+            const char* src = base[f] + (size_t)s.atom0 * 3 * elt;
+            CK(cudaMemcpy2DAsync(s.dstage[b][f], width, src, pitch, width, (size_t)nframes,
+                                 cudaMemcpyHostToDevice, s.s_copy));
+        }
+        CK(cudaEventRecord(s.ev_copy_done[b], s.s_copy));
+        if (slab_index >= 0) CK(cudaEventRecord(s.ev_slab[slab_index], s.s_copy));
+        CK(cudaStreamWaitEvent(s.s_compute, s.ev_copy_done[b], 0));
+        dim3 block(32, 8);
+        dim3 grid((unsigned)((s.natoms + K0_AT - 1) / K0_AT), (unsigned)((nframes + K0_FR - 1) / K0_FR));
+        const int d0 = ctx->dims[0], d1 = ctx->dims[1], d2 = ctx->dims[2];
+        const bool hel = ctx->n_fields == 2;
+        if (ctx->src_dtype == TA_DTYPE_F32) {
+            const float* v = (const float*)s.dstage[b][0];
+            const float* x = (const float*)s.dstage[b][1];
+            if (hel) k0_stage<float, true><<<grid, block, 0, s.s_compute>>>(v, x, s.masses, s.series, (int)s.natoms, (int)nframes, frame0, ctx->Tld, ctx->D, d0, d1, d2);
+            else k0_stage<float, false><<<grid, block, 0, s.s_compute>>>(v, x, s.masses, s.series, (int)s.natoms, (int)nframes, frame0, ctx->Tld, ctx->D, d0, d1, d2);
+        } else {
+            const double* v = (const double*)s.dstage[b][0];
+            const double* x = (const double*)s.dstage[b][1];
+            if (hel) k0_stage<double, true><<<grid, block, 0, s.s_compute>>>(v, x, s.masses, s.series, (int)s.natoms, (int)nframes, frame0, ctx->Tld, ctx->D, d0, d1, d2);
+            else k0_stage<double, false><<<grid, block, 0, s.s_compute>>>(v, x, s.masses, s.series, (int)s.natoms, (int)nframes, frame0, ctx->Tld, ctx->D, d0, d1, d2);
+        }
+        CK(cudaGetLastError());
+        ctx->launches++;
+        CK(cudaEventRecord(s.ev_k0_done[b], s.s_compute));
+    }
+    ctx->frames_staged += nframes;
+    return TA_OK;
+}
+
+int ensure_partial(ta_ctx* ctx, Shard& s, size_t rows) {
+    if (s.partial_rows < rows) {
+        cudaFree(s.partial);
+        s.partial = nullptr;
+        s.partial_rows = 0;
+        CK(cudaMalloc(&s.partial, rows * (size_t)ctx->Tld * sizeof(double)));
+        s.partial_rows = rows;
+    }
+    CK(cudaMemsetAsync(s.partial, 0, rows * (size_t)ctx->Tld * sizeof(double), s.s_compute));
+    return TA_OK;
+}
+
+// Sum the per-CTA partial rows, all-reduce over devices / ranks, divide by the
+// total particle count: results.timeseries = by_particle.mean(axis=1)
+// (velocityautocorr.py:214,237; viscosity.py:233).
+int finish_timeseries(ta_ctx* ctx, const std::vector<int>& grids, double* ts_out) {
+    const int T = (int)ctx->T;
+    const size_t cnt = (size_t)ctx->Tld + 1;   // + particle count in the last slot
+    for (size_t i = 0; i < ctx->sh.size(); ++i) {
+        Shard& s = ctx->sh[i];
+        CK(cudaSetDevice(s.dev));
+        CK(cudaMemsetAsync(s.ts_sum, 0, cnt * sizeof(double), s.s_compute));
+        if (s.natoms > 0) {
+            k_sum_partials<<<(T + 255) / 256, 256, 0, s.s_compute>>>(s.partial, grids[i], ctx->Tld, T, s.ts_sum);
+            CK(cudaGetLastError());
+            ctx->launches++;
+        }
+        s.natoms_d = (double)s.natoms;
+        CK(cudaMemcpyAsync(s.ts_sum + ctx->Tld, &s.natoms_d, sizeof(double), cudaMemcpyHostToDevice, s.s_compute));
+    }
+    if (ctx->have_comm) {
+        CKN(g_nccl.GroupStart());
+        for (auto& s : ctx->sh) {
+            ncclResult_t r = g_nccl.AllReduce(s.ts_sum, s.ts_sum, cnt, ncclDouble, ncclSum, s.comm, s.s_compute);
+            if (r != ncclSuccess) {
+                g_nccl.GroupEnd();
+                return fail(ctx, TA_ERR_NCCL, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r));
+            }
+        }
+        CKN(g_nccl.GroupEnd());
+    }
+    Shard& s0 = ctx->sh[0];
+    ctx->host_ts.resize(cnt);
+    CK(cudaSetDevice(s0.dev));
+    CK(cudaMemcpyAsync(ctx->host_ts.data(), s0.ts_sum, cnt * sizeof(double), cudaMemcpyDeviceToHost, s0.s_compute));
+    int rc = sync_all(ctx);
+    if (rc) return rc;
+    const double ntot = ctx->host_ts[ctx->Tld];
+    for (int k = 0; k < T; ++k) ts_out[k] = ctx->host_ts[k] / ntot;
+    return TA_OK;
+}
+
+int check_ready(ta_ctx* ctx) {
+    if (!ctx) return fail(nullptr, TA_ERR_INVALID, "null context");
+    if (!ctx->begun) return fail(ctx, TA_ERR_INVALID, "ta_stage_begin has not been called");
+    if (ctx->frames_staged < ctx->T)
+        return fail(ctx, TA_ERR_INVALID, "only " + std::to_string(ctx->frames_staged) + " of " +
+                                             std::to_string(ctx->T) + " frames were staged");
+    return TA_OK;
+}
+
+template <typename R>
+int upload_fft_tables(ta_ctx* ctx, const std::vector<uint32_t>& own0) {
+    const FftPlanHost& p = ctx->plan;
+    const int nlo = 1 << p.lo_bits, nhi = (int)p.tw_hi.size() / 2;
+    std::vector<cplx<R>> lo(nlo), hi(nhi);
+    for (int i = 0; i < nlo; ++i) lo[i] = cmake<R>((R)p.tw_lo[2 * i], (R)p.tw_lo[2 * i + 1]);
+    for (int i = 0; i < nhi; ++i) hi[i] = cmake<R>((R)p.tw_hi[2 * i], (R)p.tw_hi[2 * i + 1]);
+    for (auto& s : ctx->sh) {
+        CK(cudaSetDevice(s.dev));
+        cudaFree(s.tw_lo); cudaFree(s.tw_hi); cudaFree(s.ftab); cudaFree(s.pair0); cudaFree(s.own0);
+        s.tw_lo = s.tw_hi = nullptr; s.ftab = s.pair0 = s.own0 = nullptr;
+        CK(cudaMalloc(&s.tw_lo, lo.size() * sizeof(cplx<R>)));
+        CK(cudaMalloc(&s.tw_hi, hi.size() * sizeof(cplx<R>)));
+        CK(cudaMalloc(&s.ftab, p.ftab.size() * sizeof(uint32_t)));
+        CK(cudaMalloc(&s.pair0, p.pair0.size() * sizeof(uint32_t)));
+        CK(cudaMalloc(&s.own0, own0.size() * sizeof(uint32_t)));
+        CK(cudaMemcpy(s.tw_lo, lo.data(), lo.size() * sizeof(cplx<R>), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(s.tw_hi, hi.data(), hi.size() * sizeof(cplx<R>), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(s.ftab, p.ftab.data(), p.ftab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(s.pair0, p.pair0.data(), p.pair0.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(s.own0, own0.data(), own0.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    return TA_OK;
+}
+
+int ensure_fft_plan(ta_ctx* ctx) {
+    if (ctx->plan_T == ctx->T && ctx->plan_prec == ctx->precision) return TA_OK;
+    int rc = ta_build_fft_plan(ctx->T, &ctx->plan);
+    if (rc) return fail(ctx, rc, "cannot plan an FFT for T=" + std::to_string(ctx->T));
+    std::vector<uint32_t> own0;
+    for (int p = 0; p < ctx->plan.H; ++p)
+        if ((uint32_t)p <= ctx->plan.pair0[p]) own0.push_back((uint32_t)p);
+    ctx->npairs0 = (int)own0.size();
+    rc = (ctx->precision == TA_PRECISION_FP64) ? upload_fft_tables<double>(ctx, own0)
+                                               : upload_fft_tables<float>(ctx, own0);
+    if (rc) return rc;
+    ctx->plan_T = ctx->T;
+    ctx->plan_prec = ctx->precision;
+    return TA_OK;
+}
+
+template <typename R>
+int launch_fft(ta_ctx* ctx, std::vector<int>* grids) {
+    const FftPlanHost& p = ctx->plan;
+    const int nlo = 1 << p.lo_bits, nhi = (int)p.tw_hi.size() / 2;
+    size_t smem = (size_t)p.H * sizeof(cplx<R>) + (size_t)(nlo + nhi) * sizeof(cplx<R>) +
+                  (size_t)(p.H + 1) * sizeof(R);
+    smem = (smem + 15) & ~(size_t)15;
+    int nthr = ((p.H / 8 + 31) / 32) * 32;
+    nthr = std::max(32, std::min(K1_MAX_THREADS, nthr));
+    grids->assign(ctx->sh.size(), 0);
+    for (size_t i = 0; i < ctx->sh.size(); ++i) {
+        Shard& s = ctx->sh[i];
+        if (s.natoms == 0) continue;
+        CK(cudaSetDevice(s.dev));
+        if (smem > (size_t)s.max_smem)
+            return fail(ctx, TA_ERR_UNSUPPORTED,
+                        "FFT route: T=" + std::to_string(ctx->T) + " needs " + std::to_string(smem) +
+                            " B of shared memory per CTA (limit " + std::to_string(s.max_smem) +
+                            "); use fft=False or precision fp32");
+        CK(cudaFuncSetAttribute(k1_fft_acf<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1_fft_acf<R>, nthr, smem));
+        if (occ < 1) return fail(ctx, TA_ERR_UNSUPPORTED, "FFT kernel does not fit on an SM");
+        int grid = (int)std::min<int64_t>(s.natoms, (int64_t)s.num_sms * occ);
+        (*grids)[i] = grid;
+        int rc = ensure_partial(ctx, s, (size_t)grid);
+        if (rc) return rc;
+        K1Args<R> a;
+        a.t.T = (int)ctx->T; a.t.H = p.H; a.t.L = p.L; a.t.npasses = p.npasses;
+        for (int q = 0; q < TA_MAX_PASSES; ++q) a.t.radix[q] = p.radix[q];
+        a.t.lo_bits = p.lo_bits;
+        a.t.tw_lo = (const cplx<R>*)s.tw_lo;
+        a.t.tw_hi = (const cplx<R>*)s.tw_hi;
+        a.t.ftab = s.ftab; a.t.pair0 = s.pair0; a.t.own0 = s.own0; a.t.npairs0 = ctx->npairs0;
+        a.nlo = nlo; a.nhi = nhi;
+        a.series = s.series; a.by_particle = s.by_particle; a.partial = s.partial;
+        a.natoms = (int)s.natoms; a.D = ctx->D; a.Tld = ctx->Tld;
+        k1_fft_acf<R><<<grid, nthr, smem, s.s_compute>>>(a);
+        CK(cudaGetLastError());
+        ctx->launches++;
+        ctx->k1_threads = nthr; ctx->k1_smem = (int)smem; ctx->k1_grid = grid;
+    }
+    return TA_OK;
+}
+
+template <typename R, int MODE>
+int launch_windowed(ta_ctx* ctx, double denom, std::vector<int>* grids) {
+    const int T = (int)ctx->T;
+    const int ne = win_smem_elems(T);
+    size_t smem = (size_t)((ne + 1) & ~1) * sizeof(R) + (size_t)T * sizeof(double);
+    smem = (smem + 15) & ~(size_t)15;
+    const int npairs = win_num_pairs(win_num_lag_blocks(T));
+    const int nthr = 32 * std::max(1, std::min(KW_MAX_THREADS / 32, npairs));
+    grids->assign(ctx->sh.size(), 0);
+    for (size_t i = 0; i < ctx->sh.size(); ++i) {
+        Shard& s = ctx->sh[i];
+        if (s.natoms == 0) continue;
+        CK(cudaSetDevice(s.dev));
+        if (smem > (size_t)s.max_smem)
+            return fail(ctx, TA_ERR_UNSUPPORTED,
+                        "windowed route: T=" + std::to_string(T) + " needs " + std::to_string(smem) +
+                            " B of shared memory per CTA (limit " + std::to_string(s.max_smem) + ")");
+        CK(cudaFuncSetAttribute(k_windowed<R, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_windowed<R, MODE>, nthr, smem));
+        if (occ < 1) return fail(ctx, TA_ERR_UNSUPPORTED, "windowed kernel does not fit on an SM");
+        int grid = (int)std::min<int64_t>(s.natoms, (int64_t)s.num_sms * occ);
+        (*grids)[i] = grid;
+        int rc = ensure_partial(ctx, s, (size_t)grid);
+        if (rc) return rc;
+        WinArgs a;
+        a.series = s.series; a.by_particle = s.by_particle; a.partial = s.partial;
+        a.natoms = (int)s.natoms; a.D = ctx->D; a.T = T; a.Tld = ctx->Tld; a.denom = denom;
+        k_windowed<R, MODE><<<grid, nthr, smem, s.s_compute>>>(a);
+        CK(cudaGetLastError());
+        ctx->launches++;
+    }
+    return TA_OK;
+}
+
+int create_common(ta_ctx* ctx, int ndev, const int* devices) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(ctx, TA_ERR_CUDA,
+                    std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                        "); libta_b200 has no CPU fallback");
+    if (ndev < 1) return fail(ctx, TA_ERR_INVALID, "ndev must be >= 1");
+    ctx->sh.resize(ndev);
+    for (int i = 0; i < ndev; ++i) {
+        int dev = devices ? devices[i] : i;
+        if (dev < 0 || dev >= count)
+            return fail(ctx, TA_ERR_INVALID, "device index " + std::to_string(dev) + " out of range");
+        int rc = init_shard(ctx, ctx->sh[i], dev);
+        if (rc) return rc;
+    }
+    return TA_OK;
+}
+
+void destroy_ctx(ta_ctx* c) {
+    if (!c) return;
+    free_problem(c);
+    for (auto& s : c->sh) {
+        cudaSetDevice(s.dev);
+        if (s.comm && g_nccl.handle) g_nccl.CommDestroy(s.comm);
+        for (int b = 0; b < kNumDevStage; ++b) {
+            if (s.ev_copy_done[b]) cudaEventDestroy(s.ev_copy_done[b]);
+            if (s.ev_k0_done[b]) cudaEventDestroy(s.ev_k0_done[b]);
+        }
+        for (int i = 0; i < kNumSlabs; ++i) if (s.ev_slab[i]) cudaEventDestroy(s.ev_slab[i]);
+        if (s.ev_t0) cudaEventDestroy(s.ev_t0);
+        if (s.ev_t1) cudaEventDestroy(s.ev_t1);
+        if (s.s_compute) cudaStreamDestroy(s.s_compute);
+        if (s.s_copy) cudaStreamDestroy(s.s_copy);
+    }
+    delete c;
+}
+
+}  // namespace
+
+// =============================================================== C ABI
+extern "C" {
+
+int ta_version(void) { return 100; }
+
+int ta_device_count(int* count) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    if (count) *count = n;
+    return TA_OK;
+}
+
+const char* ta_last_error(const ta_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int ta_ctx_create(int ndev, const int* devices, ta_ctx** out) {
+    if (!out) return fail(nullptr, TA_ERR_INVALID, "out is null");
+    *out = nullptr;
+    ta_ctx* ctx = new ta_ctx();
+    int rc = create_common(ctx, ndev, devices);
+    if (rc == TA_OK && ndev > 1) {
+        std::string err;
+        if (!nccl_load(&err)) rc = fail(ctx, TA_ERR_NCCL, err);
+        if (rc == TA_OK) {
+            std::vector<ncclComm_t> comms(ndev);
+            std::vector<int> devs(ndev);
+            for (int i = 0; i < ndev; ++i) devs[i] = ctx->sh[i].dev;
+            ncclResult_t r = g_nccl.CommInitAll(comms.data(), ndev, devs.data());
+            if (r != ncclSuccess) rc = fail(ctx, TA_ERR_NCCL, std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(r));
+            else {
+                for (int i = 0; i < ndev; ++i) ctx->sh[i].comm = comms[i];
+                ctx->have_comm = true;
+            }
+        }
+    }
+    if (rc != TA_OK) {
+        g_last_error = ctx->err;
+        destroy_ctx(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return TA_OK;
+}
+
+int ta_nccl_unique_id(void* id128) {
+    std::string err;
+    if (!id128) return fail(nullptr, TA_ERR_INVALID, "id128 is null");
+    if (!nccl_load(&err)) return fail(nullptr, TA_ERR_NCCL, err);
+    static_assert(sizeof(ncclUniqueId) == TA_NCCL_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(nullptr, TA_ERR_NCCL, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r));
+    memcpy(id128, &id, sizeof(id));
+    return TA_OK;
+}
+
+int ta_ctx_create_rank(int device, int rank, int nranks, const void* id128, ta_ctx** out) {
+    if (!out) return fail(nullptr, TA_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(nullptr, TA_ERR_INVALID, "bad rank / nranks");
+    ta_ctx* ctx = new ta_ctx();
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    int rc = create_common(ctx, 1, &device);
+    if (rc == TA_OK && nranks > 1) {
+        std::string err;
+        if (!id128) rc = fail(ctx, TA_ERR_INVALID, "id128 is null");
+        else if (!nccl_load(&err)) rc = fail(ctx, TA_ERR_NCCL, err);
+        else {
+            ncclUniqueId id;
+            memcpy(&id, id128, sizeof(id));
+            cudaSetDevice(ctx->sh[0].dev);
+            ncclResult_t r = g_nccl.CommInitRank(&ctx->sh[0].comm, nranks, id, rank);
+            if (r != ncclSuccess) rc = fail(ctx, TA_ERR_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
+            else ctx->have_comm = true;
+        }
+    }
+    if (rc != TA_OK) {
+        g_last_error = ctx->err;
+        destroy_ctx(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return TA_OK;
+}
+
+void ta_ctx_destroy(ta_ctx* ctx) { destroy_ctx(ctx); }
+
+int ta_host_register(void* ptr, uint64_t bytes) {
+    ta_ctx* ctx = nullptr;
+    CK(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+    return TA_OK;
+}
+int ta_host_unregister(void* ptr) {
+    ta_ctx* ctx = nullptr;
+    CK(cudaHostUnregister(ptr));
+    return TA_OK;
+}
+
+int ta_stage_begin(ta_ctx* ctx, int64_t T, int64_t N, int D, const int* dims, int src_dtype,
+                   int n_fields, const double* masses, int precision) {
+    if (!ctx) return fail(nullptr, TA_ERR_INVALID, "null context");
+    if (T < 1 || N < 0) return fail(ctx, TA_ERR_INVALID, "T must be >= 1 and N >= 0");
+    if (T > (int64_t)1 << 24) return fail(ctx, TA_ERR_UNSUPPORTED, "T too large");
+    if (D < 1 || D > 3 || !dims) return fail(ctx, TA_ERR_INVALID, "D must be 1..3 with dims given");
+    for (int i = 0; i < D; ++i)
+        if (dims[i] < 0 || dims[i] > 2) return fail(ctx, TA_ERR_INVALID, "dims entries must be 0, 1 or 2");
+    if (src_dtype != TA_DTYPE_F32 && src_dtype != TA_DTYPE_F64) return fail(ctx, TA_ERR_INVALID, "bad src_dtype");
+    if (n_fields != 1 && n_fields != 2) return fail(ctx, TA_ERR_INVALID, "n_fields must be 1 or 2");
+    if (n_fields == 2 && !masses && N > 0) return fail(ctx, TA_ERR_INVALID, "masses are required with n_fields == 2");
+    if (precision != TA_PRECISION_FP64 && precision != TA_PRECISION_FP32) return fail(ctx, TA_ERR_INVALID, "bad precision");
+    free_problem(ctx);
+    ctx->T = T; ctx->N = N; ctx->D = D;
+    for (int i = 0; i < 3; ++i) ctx->dims[i] = (i < D) ? dims[i] : 0;
+    ctx->src_dtype = src_dtype;
+    ctx->elt = (src_dtype == TA_DTYPE_F32) ? 4 : 8;
+    ctx->n_fields = n_fields;
+    ctx->precision = precision;
+    ctx->Tld = ((T + 15) / 16) * 16;
+
+    // pinned slab ring: ~32 MB per slab, at most 512 frames
+    const size_t frame_bytes = (size_t)n_fields * (size_t)std::max<int64_t>(N, 1) * 3 * ctx->elt;
+    int64_t F = (int64_t)((32u << 20) / frame_bytes);
+    F = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(F, 512), T));
+    ctx->slab_frames = F;
+
+    const int ndev = (int)ctx->sh.size();
+    const int64_t base = N / ndev, rem = N % ndev;
+    int64_t a0 = 0;
+    for (int i = 0; i < ndev; ++i) {
+        Shard& s = ctx->sh[i];
+        s.atom0 = a0;
+        s.natoms = base + (i < rem ? 1 : 0);
+        a0 += s.natoms;
+        s.stage_toggle = 0;
+        CK(cudaSetDevice(s.dev));
+        CK(cudaMalloc(&s.ts_sum, ((size_t)ctx->Tld + 16) * sizeof(double)));
+        if (s.natoms == 0) continue;
+        const size_t ser_bytes = (size_t)s.natoms * D * ctx->Tld * sizeof(double);
+        const size_t out_bytes = (size_t)s.natoms * ctx->Tld * sizeof(double);
+        cudaError_t e = cudaMalloc(&s.series, ser_bytes);
+        if (e == cudaSuccess) e = cudaMalloc(&s.by_particle, out_bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            free_problem(ctx);
+            return fail(ctx, TA_ERR_NOMEM, "device " + std::to_string(s.dev) + ": cannot allocate " +
+                                               std::to_string((ser_bytes + out_bytes) >> 20) + " MiB for series + results");
+        }
+        CK(cudaMemsetAsync(s.series, 0, ser_bytes, s.s_compute));
+        CK(cudaMemsetAsync(s.by_particle, 0, out_bytes, s.s_compute));
+        if (n_fields == 2) {
+            CK(cudaMalloc(&s.masses, (size_t)s.natoms * sizeof(double)));
+            CK(cudaMemcpyAsync(s.masses, masses + s.atom0, (size_t)s.natoms * sizeof(double), cudaMemcpyHostToDevice, s.s_compute));
+        }
+        for (int b = 0; b < kNumDevStage; ++b)
+            for (int f = 0; f < n_fields; ++f)
+                CK(cudaMalloc(&s.dstage[b][f], (size_t)F * s.natoms * 3 * ctx->elt));
+        // events start "signalled": record them once on an idle stream
+        for (int b = 0; b < kNumDevStage; ++b) {
+            CK(cudaEventRecord(s.ev_k0_done[b], s.s_compute));
+            CK(cudaEventRecord(s.ev_copy_done[b], s.s_copy));
+        }
+    }
+    ctx->begun = true;
+    return sync_all(ctx);
+}
+
+int ta_stage_slot(ta_ctx* ctx, void** host_ptr, int64_t* frames_capacity) {
+    if (!ctx || !ctx->begun) return fail(ctx, TA_ERR_INVALID, "ta_stage_begin has not been called");
+    if (!host_ptr) return fail(ctx, TA_ERR_INVALID, "host_ptr is null");
+    const int i = ctx->next_slab;
+    if (!ctx->slab[i]) {
+        const size_t bytes = (size_t)ctx->slab_frames * ctx->n_fields * (size_t)std::max<int64_t>(ctx->N, 1) * 3 * ctx->elt;
+        CK(cudaHostAlloc(&ctx->slab[i], bytes, cudaHostAllocPortable));
+    } else if (ctx->slab_used[i]) {
+        for (auto& s : ctx->sh) {   // H2D copies that read this slab must have finished
+            if (s.natoms == 0) continue;
+            CK(cudaSetDevice(s.dev));
+            CK(cudaEventSynchronize(s.ev_slab[i]));
+        }
+    }
+    ctx->cur_slab = i;
+    ctx->next_slab = (i + 1) % kNumSlabs;
+    *host_ptr = ctx->slab[i];
+    if (frames_capacity) *frames_capacity = ctx->slab_frames;
+    return TA_OK;
+}
+
+int ta_stage_commit(ta_ctx* ctx, int64_t frame0, int64_t nframes) {
+    if (!ctx || !ctx->begun) return fail(ctx, TA_ERR_INVALID, "ta_stage_begin has not been called");
+    if (ctx->cur_slab < 0) return fail(ctx, TA_ERR_INVALID, "ta_stage_commit without ta_stage_slot");
+    if (nframes < 1 || nframes > ctx->slab_frames || frame0 < 0 || frame0 + nframes > ctx->T)
+        return fail(ctx, TA_ERR_INVALID, "frame range outside [0, T) or larger than the slab");
+    const size_t row = (size_t)ctx->N * 3 * ctx->elt;
+    const char* base[2];
+    base[0] = (const char*)ctx->slab[ctx->cur_slab];
+    base[1] = base[0] + row;
+    const int slab = ctx->cur_slab;
+    ctx->slab_used[slab] = true;
+    ctx->cur_slab = -1;
+    return enqueue_chunk(ctx, base, (size_t)ctx->n_fields * row, frame0, nframes, slab);
+}
+
+int ta_stage_bulk(ta_ctx* ctx, const void* const* fields, int64_t src_atoms, int64_t atom_first,
+                  int64_t frame_first, int64_t frame_step, int64_t nframes) {
+    if (!ctx || !ctx->begun) return fail(ctx, TA_ERR_INVALID, "ta_stage_begin has not been called");
+    if (!fields || !fields[0] || (ctx->n_fields == 2 && !fields[1])) return fail(ctx, TA_ERR_INVALID, "field pointer is null");
+    if (nframes != ctx->T) return fail(ctx, TA_ERR_INVALID, "ta_stage_bulk must deliver all T frames");
+    if (frame_step < 1 || frame_first < 0 || atom_first < 0 || atom_first + ctx->N > src_atoms)
+        return fail(ctx, TA_ERR_INVALID, "bad frame / atom window");
+    const size_t src_row = (size_t)src_atoms * 3 * ctx->elt;
+    const size_t pitch = (size_t)frame_step * src_row;
+    for (int64_t f0 = 0; f0 < nframes; f0 += ctx->slab_frames) {
+        const int64_t nf = std::min<int64_t>(ctx->slab_frames, nframes - f0);
+        const char* base[2] = {nullptr, nullptr};
+        for (int f = 0; f < ctx->n_fields; ++f)
+            base[f] = (const char*)fields[f] + (size_t)(frame_first + f0 * frame_step) * src_row +
+                      (size_t)atom_first * 3 * ctx->elt;
+        int rc = enqueue_chunk(ctx, base, pitch, f0, nf, -1);
+        if (rc) return rc;
+    }
+    return TA_OK;
+}
+
+int ta_stage_end(ta_ctx* ctx) {
+    if (!ctx || !ctx->begun) return fail(ctx, TA_ERR_INVALID, "ta_stage_begin has not been called");
+    return sync_all(ctx);
+}
+
+int ta_vacf_fft(ta_ctx* ctx, double* ts_out) {
+    int rc = check_ready(ctx);
+    if (rc) return rc;
+    if (!ts_out) return fail(ctx, TA_ERR_INVALID, "ts_out is null");
+    if ((rc = ensure_fft_plan(ctx))) return rc;
+    std::vector<int> grids;
+    rc = (ctx->precision == TA_PRECISION_FP64) ? launch_fft<double>(ctx, &grids) : launch_fft<float>(ctx, &grids);
+    if (rc) return rc;
+    return finish_timeseries(ctx, grids, ts_out);
+}
+
+int ta_vacf_windowed(ta_ctx* ctx, double* ts_out) {
+    int rc = check_ready(ctx);
+    if (rc) return rc;
+    if (!ts_out) return fail(ctx, TA_ERR_INVALID, "ts_out is null");
+    std::vector<int> grids;
+    rc = (ctx->precision == TA_PRECISION_FP64) ? launch_windowed<double, TA_WIN_PRODUCT>(ctx, 1.0, &grids)
+                                               : launch_windowed<float, TA_WIN_PRODUCT>(ctx, 1.0, &grids);
+    if (rc) return rc;
+    return finish_timeseries(ctx, grids, ts_out);
+}
+
+int ta_helfand(ta_ctx* ctx, const double* volumes, double boltzmann, double temp_avg, double* ts_out) {
+    int rc = check_ready(ctx);
+    if (rc) return rc;
+    if (!ts_out || !volumes) return fail(ctx, TA_ERR_INVALID, "volumes / ts_out is null");
+    if (ctx->n_fields != 2) return fail(ctx, TA_ERR_INVALID, "ta_helfand needs velocities and positions (n_fields == 2)");
+    double vsum = 0.0;
+    for (int64_t i = 0; i < ctx->T; ++i) vsum += volumes[i];
+    const double vol_avg = vsum / (double)ctx->T;                 // viscosity.py:205
+    const double denom = 2 * boltzmann * vol_avg * temp_avg;      // viscosity.py:229-231
+    std::vector<int> grids;
+    rc = (ctx->precision == TA_PRECISION_FP64) ? launch_windowed<double, TA_WIN_SQDIFF>(ctx, denom, &grids)
+                                               : launch_windowed<float, TA_WIN_SQDIFF>(ctx, denom, &grids);
+    if (rc) return rc;
+    return finish_timeseries(ctx, grids, ts_out);
+}
+
+int ta_fetch_by_particle(ta_ctx* ctx, int64_t atom0, int64_t natoms, int layout, double* out) {
+    if (!ctx || !ctx->begun) return fail(ctx, TA_ERR_INVALID, "ta_stage_begin has not been called");
+    if (!out || atom0 < 0 || natoms < 0 || atom0 + natoms > ctx->N) return fail(ctx, TA_ERR_INVALID, "bad particle range");
+    if (layout != TA_LAYOUT_ATOM_MAJOR && layout != TA_LAYOUT_LAG_MAJOR) return fail(ctx, TA_ERR_INVALID, "bad layout");
+    const int64_t T = ctx->T, Tld = ctx->Tld;
+    for (auto& s : ctx->sh) {
+        const int64_t lo = std::max(atom0, s.atom0), hi = std::min(atom0 + natoms, s.atom0 + s.natoms);
+        if (lo >= hi) continue;
+        CK(cudaSetDevice(s.dev));
+        CK(cudaStreamSynchronize(s.s_compute));
+        if (layout == TA_LAYOUT_ATOM_MAJOR) {
+            CK(cudaMemcpy2D(out + (size_t)(lo - atom0) * T, (size_t)T * 8, s.by_particle + (size_t)(lo - s.atom0) * Tld,
+                            (size_t)Tld * 8, (size_t)T * 8, (size_t)(hi - lo), cudaMemcpyDeviceToHost));
+        } else {
+            const int64_t chunk = std::max<int64_t>(32, ((int64_t)(64u << 20) / (T * 8)) / 32 * 32);
+            const size_t need = (size_t)std::min<int64_t>(chunk, hi - lo) * T * 8;
+            if (s.lagmajor_bytes < need) {
+                cudaFree(s.lagmajor_tmp);
+                s.lagmajor_tmp = nullptr; s.lagmajor_bytes = 0;
+                CK(cudaMalloc(&s.lagmajor_tmp, need));
+                s.lagmajor_bytes = need;
+            }
+            for (int64_t c0 = lo; c0 < hi; c0 += chunk) {
+                const int64_t cn = std::min<int64_t>(chunk, hi - c0);
+                dim3 block(32, 8), grid((unsigned)((T + 31) / 32), (unsigned)((cn + 31) / 32));
+                k_to_lag_major<<<grid, block, 0, s.s_compute>>>(s.by_particle, Tld, (int)T, c0 - s.atom0, (int)cn, s.lagmajor_tmp);
+                CK(cudaGetLastError());
+                ctx->launches++;
+                CK(cudaMemcpy2DAsync(out + (size_t)(c0 - atom0), (size_t)natoms * 8, s.lagmajor_tmp, (size_t)cn * 8,
+                                     (size_t)cn * 8, (size_t)T, cudaMemcpyDeviceToHost, s.s_compute));
+                CK(cudaStreamSynchronize(s.s_compute));
+            }
+        }
+    }
+    return TA_OK;
+}
+
+int ta_timer_begin(ta_ctx* ctx) {
+    if (!ctx) return fail(nullptr, TA_ERR_INVALID, "null context");
+    for (auto& s : ctx->sh) {
+        CK(cudaSetDevice(s.dev));
+        CK(cudaEventRecord(s.ev_t0, s.s_compute));
+    }
+    return TA_OK;
+}
+
+int ta_timer_end(ta_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return fail(ctx, TA_ERR_INVALID, "null argument");
+    float worst = 0.f;
+    for (auto& s : ctx->sh) {
+        CK(cudaSetDevice(s.dev));
+        CK(cudaStreamSynchronize(s.s_copy));
+        CK(cudaEventRecord(s.ev_t1, s.s_compute));
+        CK(cudaEventSynchronize(s.ev_t1));
+        float t = 0.f;
+        CK(cudaEventElapsedTime(&t, s.ev_t0, s.ev_t1));
+        worst = std::max(worst, t);
+    }
+    *ms = worst;
+    return TA_OK;
+}
+
+int64_t ta_launch_count(const ta_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ta_fft_plan_info(const ta_ctx* ctx, int* H, int* npasses, int* radices, int* threads, int* smem_bytes, int* grid) {
+    if (!ctx) return TA_ERR_INVALID;
+    const bool have = ctx->plan_T >= 0;
+    if (H) *H = have ? ctx->plan.H : 0;
+    if (npasses) *npasses = have ? ctx->plan.npasses : 0;
+    if (radices) for (int i = 0; i < TA_MAX_PASSES; ++i) radices[i] = have ? ctx->plan.radix[i] : 0;
+    if (threads) *threads = ctx->k1_threads;
+    if (smem_bytes) *smem_bytes = ctx->k1_smem;
+    if (grid) *grid = ctx->k1_grid;
+    return TA_OK;
+}
+
+}  // extern "C"
