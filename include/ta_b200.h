@@ -112,6 +112,13 @@ int ta_fetch_by_particle(ta_ctx* ctx, int64_t atom0, int64_t natoms, int layout,
  * events on every shard's compute stream; ms = max over local devices). */
 int ta_timer_begin(ta_ctx* ctx);
 int ta_timer_end(ta_ctx* ctx, float* ms);
+/* Device time of the dominant kernel (K1, K2 or K3) of the last compute call,
+ * from CUDA events recorded around that launch on its own stream (max over
+ * local devices). */
+int ta_last_kernel_ms(ta_ctx* ctx, float* ms);
+/* Overwrite a 512 MB scratch buffer so that nothing of the inputs stays in L2
+ * (benchmark hygiene for workloads smaller than the 126 MB L2). */
+int ta_flush_l2(ta_ctx* ctx);
 /* Introspection for bench / tests: kernel launches issued by this context so
  * far, and the plan chosen for the FFT route (0s before the first call). */
 int64_t ta_launch_count(const ta_ctx* ctx);

@@ -42,6 +42,8 @@ _SIGNATURES = {
     "ta_fetch_by_particle": (c_int, [c_void_p, c_int64, c_int64, c_int, POINTER(c_double)]),
     "ta_timer_begin": (c_int, [c_void_p]),
     "ta_timer_end": (c_int, [c_void_p, POINTER(c_float)]),
+    "ta_last_kernel_ms": (c_int, [c_void_p, POINTER(c_float)]),
+    "ta_flush_l2": (c_int, [c_void_p]),
     "ta_launch_count": (c_int64, [c_void_p]),
     "ta_fft_plan_info": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int),
                                  POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
@@ -236,6 +238,14 @@ class Context:
         ms = c_float()
         self._check(self._lib.ta_timer_end(self._h, ctypes.byref(ms)), "ta_timer_end")
         return float(ms.value)
+
+    def last_kernel_ms(self) -> float:
+        ms = c_float()
+        self._check(self._lib.ta_last_kernel_ms(self._h, ctypes.byref(ms)), "ta_last_kernel_ms")
+        return float(ms.value)
+
+    def flush_l2(self):
+        self._check(self._lib.ta_flush_l2(self._h), "ta_flush_l2")
 
     def launch_count(self) -> int:
         return int(self._lib.ta_launch_count(self._h))

@@ -17,6 +17,8 @@ from . import _lib
 
 
 def resolve_devices(devices):
+    if isinstance(devices, _lib.Context):
+        return devices          # an open context to run on (bench.py's multi-rank mode)
     if devices is None:
         env = os.environ.get("TA_B200_DEVICES")
         if env:
@@ -59,8 +61,12 @@ class FrameStager:
 
     def __init__(self, devices, n_frames: int, n_particles: int, dim_cols, n_fields: int,
                  masses, precision: str):
-        self._devices = devices
-        self._ctx = None
+        # `devices`: device ids, or an already open Context to reuse (a second
+        # run() on the same analysis object keeps its device buffers)
+        if isinstance(devices, _lib.Context):
+            self._devices, self._ctx = None, devices
+        else:
+            self._devices, self._ctx = devices, None
         self.T, self.N = int(n_frames), int(n_particles)
         self.dim_cols, self.n_fields = list(dim_cols), n_fields
         self.masses, self.precision = masses, precision

@@ -92,10 +92,7 @@ class VelocityAutocorr(AnalysisBase):
     def _prepare(self):
         if self.n_frames < 1 or self.n_particles < 1:
             raise ValueError("VACF needs at least one frame and one particle")
-        if self._ctx is not None:
-            self._ctx.close()
-            self._ctx = None
-        self._stager = FrameStager(self._devices, self.n_frames, self.n_particles, self._dim, 1, None,
+        self._stager = FrameStager(self._ctx or self._devices, self.n_frames, self.n_particles, self._dim, 1, None,
                                    self.precision)
         self._stager.try_bulk(self._trajectory, self.atomgroup.ix, getattr(self, "start", None),
                               getattr(self, "stop", None), getattr(self, "step", None), False)

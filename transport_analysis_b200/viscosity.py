@@ -67,10 +67,7 @@ class ViscosityHelfand(AnalysisBase):
             self.boltzmann = constants["Boltzmann_constant"]
         except KeyError:
             self.boltzmann = constants["Boltzman_constant"]
-        if self._ctx is not None:
-            self._ctx.close()
-            self._ctx = None
-        self._stager = FrameStager(self._devices, self.n_frames, self.n_particles, self._dim, 2,
+        self._stager = FrameStager(self._ctx or self._devices, self.n_frames, self.n_particles, self._dim, 2,
                                    self._masses, self.precision)
         reader = self._trajectory
         # the bulk path still needs a box volume for every frame
