@@ -10,6 +10,8 @@
 #include "../../transport_analysis_b200/csrc/fft_plan.h"
 #include "../../transport_analysis_b200/csrc/fft_core.cuh"
 #include "../../transport_analysis_b200/csrc/windowed_core.cuh"
+#include "../../transport_analysis_b200/csrc/k1_fast.cuh"
+#include "fiber_cta.h"
 
 using namespace ta;
 
@@ -86,7 +88,42 @@ static int run_win(const double* series, int T, int D, int Tld, int mode, int nw
     return 0;
 }
 
+template <int R1>
+static int run_k1fast(const double* series, int T, int D, int Tld, int natoms, int nblk, double* by_particle,
+                      double* partial) {
+    K1FastPlan p;
+    int rc = k1f_build_plan(T, Tld, R1, &p);
+    if (rc) return rc;
+    K1FArgs a;
+    a.series = series; a.by_particle = by_particle; a.partial = partial;
+    a.omega = reinterpret_cast<const cd*>(p.omega.data());
+    a.tw2 = reinterpret_cast<const cd*>(p.tw2.data());
+    a.map = p.map.data();
+    a.wbase = reinterpret_cast<const cd*>(p.wbase.data());
+    a.inv = p.inv.data();
+    a.natoms = natoms; a.D = D; a.T = T; a.nh = p.nh; a.Tld = Tld;
+    std::vector<unsigned char> smem(k1f_smem_bytes(R1) + 64);
+    unsigned char* sm = smem.data() + (16 - ((uintptr_t)smem.data() & 15)) % 16;
+    for (int bid = 0; bid < nblk; ++bid)
+        emu::run_cta(16 * R1, [&](int tid) { k1f_body<R1, emu::EmuCtx>(a, sm, tid, bid, nblk); });
+    return 0;
+}
+
 extern "C" {
+int emu_k1fast_r1(int T) { return k1f_choose_r1(T); }
+int emu_k1fast(const double* series, int T, int D, int Tld, int natoms, int nblk, int R1, double* by_particle,
+               double* partial) {
+    switch (R1) {
+        case 4: return run_k1fast<4>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 6: return run_k1fast<6>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 8: return run_k1fast<8>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 10: return run_k1fast<10>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 12: return run_k1fast<12>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 16: return run_k1fast<16>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 20: return run_k1fast<20>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+    }
+    return -1;
+}
 int emu_fft_acf(const double* series, int T, int D, int Tld, int nthr, int use_f32, double* row, double* partial) {
     return use_f32 ? run_fft<float>(series, T, D, Tld, nthr, row, partial)
                    : run_fft<double>(series, T, D, Tld, nthr, row, partial);

@@ -1,0 +1,121 @@
+// Cooperative-fiber emulation of one CUDA thread block on the CPU (TEST
+// INFRASTRUCTURE ONLY).  Every CUDA thread is a ucontext fiber; __syncthreads
+// and warp shuffles are barriers at which a fiber yields to a round-robin
+// scheduler.  This lets kernel bodies written against a `Ctx` policy
+// (sync / shfl_xor16) run unmodified under g++.
+#pragma once
+#include <ucontext.h>
+#include <cstdlib>
+#include <functional>
+#include <vector>
+
+namespace emu {
+
+struct Cta {
+    int nthreads = 0;
+    int current = -1;
+    std::vector<ucontext_t> ctx;
+    std::vector<char*> stacks;
+    std::vector<char> done;
+    ucontext_t sched;
+    // block barrier
+    int bar_count = 0, bar_gen = 0;
+    // per-warp shuffle state
+    std::vector<double> slot;       // [nthreads]
+    std::vector<int> w_count, w_gen; // [nwarps]
+    std::function<void(int)> body;
+};
+
+inline Cta*& active() {
+    static thread_local Cta* c = nullptr;
+    return c;
+}
+
+inline void yield_now() {
+    Cta* c = active();
+    swapcontext(&c->ctx[c->current], &c->sched);
+}
+
+inline void trampoline() {
+    Cta* c = active();
+    const int tid = c->current;
+    c->body(tid);
+    c->done[tid] = 1;
+    swapcontext(&c->ctx[tid], &c->sched);
+}
+
+inline void run_cta(int nthreads, std::function<void(int)> body, size_t stack_bytes = 512 * 1024) {
+    Cta c;
+    c.nthreads = nthreads;
+    c.ctx.resize(nthreads);
+    c.stacks.resize(nthreads);
+    c.done.assign(nthreads, 0);
+    c.slot.assign(nthreads, 0.0);
+    const int nwarps = (nthreads + 31) / 32;
+    c.w_count.assign(nwarps, 0);
+    c.w_gen.assign(nwarps, 0);
+    c.body = std::move(body);
+    Cta* prev = active();
+    active() = &c;
+    for (int t = 0; t < nthreads; ++t) {
+        c.stacks[t] = (char*)malloc(stack_bytes);
+        getcontext(&c.ctx[t]);
+        c.ctx[t].uc_stack.ss_sp = c.stacks[t];
+        c.ctx[t].uc_stack.ss_size = stack_bytes;
+        c.ctx[t].uc_link = &c.sched;
+        makecontext(&c.ctx[t], (void (*)())trampoline, 0);
+    }
+    int remaining = nthreads;
+    while (remaining > 0) {
+        for (int t = 0; t < nthreads; ++t) {
+            if (c.done[t] == 1) continue;
+            c.current = t;
+            swapcontext(&c.sched, &c.ctx[t]);
+            if (c.done[t] == 1) { c.done[t] = 2; --remaining; }
+        }
+        for (int t = 0; t < nthreads; ++t) if (c.done[t] == 2) c.done[t] = 1;
+    }
+    for (int t = 0; t < nthreads; ++t) free(c.stacks[t]);
+    active() = prev;
+}
+
+// __syncthreads()
+inline void sync_block() {
+    Cta* c = active();
+    const int gen = c->bar_gen;
+    if (++c->bar_count == c->nthreads) {
+        c->bar_count = 0;
+        ++c->bar_gen;
+    } else {
+        while (c->bar_gen == gen) yield_now();
+    }
+}
+
+inline void sync_warp_internal(Cta* c, int warp, int width) {
+    const int gen = c->w_gen[warp];
+    if (++c->w_count[warp] == width) {
+        c->w_count[warp] = 0;
+        ++c->w_gen[warp];
+    } else {
+        while (c->w_gen[warp] == gen) yield_now();
+    }
+}
+
+// __shfl_xor_sync(full mask, v, mask) for whole warps
+inline double shfl_xor(double v, int mask) {
+    Cta* c = active();
+    const int tid = c->current, warp = tid >> 5;
+    const int width = (c->nthreads - warp * 32) < 32 ? (c->nthreads - warp * 32) : 32;
+    c->slot[tid] = v;
+    sync_warp_internal(c, warp, width);
+    const double got = c->slot[tid ^ mask];
+    sync_warp_internal(c, warp, width);
+    return got;
+}
+
+struct EmuCtx {
+    static void sync() { sync_block(); }
+    static double shfl_xor16(double v) { return shfl_xor(v, 16); }
+};
+
+}  // namespace emu

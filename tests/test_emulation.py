@@ -82,3 +82,43 @@ def test_fp32_mode_tolerance(emu):
     assert_close_normwise(emu_fft(emu, x, f32=1), oracle.tidynamics_acf(x), 1e-5, "fp32 fft")
     prod = np.array([np.sum(x[: 2000 - k] * x[k:]) for k in range(2000)])
     assert_close_normwise(emu_win(emu, x, 0, f32=1), prod, 1e-5, "fp32 windowed")
+
+
+# ------------------------------------------------------------------ K1 fast path under the fiber emulator
+def emu_fast(lib, x, nblk=1, R1=None):
+    """x: [T, N, D].  Runs k1f_body (k1_fast.cuh) for nblk CTAs of 16*R1 fibers."""
+    T, N, D = x.shape
+    R1 = R1 or lib.emu_k1fast_r1(T)
+    assert R1 > 0
+    Tld = (T + 15) // 16 * 16
+    ser = np.zeros((N, D, Tld))
+    ser[:, :, :T] = x.transpose(1, 2, 0)
+    bp, part = np.zeros((N, Tld)), np.zeros((nblk, Tld))
+    assert lib.emu_k1fast(_p(ser), T, D, Tld, N, nblk, R1, _p(bp), _p(part)) == 0
+    assert np.all(bp[:, T:] == 0)
+    return bp[:, :T], part[:, :T]
+
+
+@pytest.mark.parametrize("T,D,N,nblk", [(1600, 2, 1, 1), (2000, 3, 2, 1), (2047, 1, 1, 1), (3000, 3, 2, 2), (4000, 1, 1, 1),
+                                        (5000, 3, 3, 2), (5001, 2, 1, 1), (6000, 3, 1, 1), (8192, 3, 1, 1), (10000, 3, 2, 1)])
+def test_fast_fft_kernel_body_matches_tidynamics_restatement(emu, T, D, N, nblk):
+    x = np.random.default_rng(T + D).standard_normal((T, N, D))
+    bp, part = emu_fast(emu, x, nblk)
+    for a in range(N):
+        assert_close_normwise(bp[a], oracle.tidynamics_acf(x[:, a, :]), 1e-12, f"T={T} atom {a}")
+    np.testing.assert_allclose(part.sum(axis=0), bp.sum(axis=0), rtol=1e-13, atol=1e-13)
+
+
+def test_fast_fft_path_selection(emu):
+    """R1 = 0 (general kernel) for tiny or badly padded lengths, else the smallest even R1 with 256 R1 >= ceil(T/2)."""
+    for T, want in [(1, 0), (700, 0), (1533, 0), (1535, 4), (2048, 4), (2049, 0), (2400, 6), (4096, 8), (5000, 10),
+                    (5001, 10), (6144, 12), (8192, 16), (10000, 20), (10240, 20), (10241, 0), (20000, 0)]:
+        assert emu.emu_k1fast_r1(T) == want, T
+
+
+def test_fast_fft_ramp_is_exact_enough(emu):
+    """Ramp data (the reference's step trajectory) has a 1e7 dynamic range; the closed form is the reference's own."""
+    T = 5001
+    x = np.repeat(np.arange(T, dtype=np.float64)[:, None, None], 3, axis=2)
+    bp, _ = emu_fast(emu, x)
+    assert_close_normwise(bp[0], oracle.characteristic_poly(T, 3), 1e-11)

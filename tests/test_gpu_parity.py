@@ -228,6 +228,40 @@ def test_lazy_by_particle(rand_u):
     assert np.array_equal(lazy.particles(4, 9), eager[:, 4:9])
 
 
+# ------------------------------------------------------------------ K1 fast path (H = 256 R1, k1_fast.cuh)
+@pytest.mark.parametrize("T,N,dim", [(1600, 5, "xyz"), (2000, 70, "xyz"), (2047, 3, "x"), (3000, 9, "yz"), (4000, 4, "xyz"),
+                                     (5000, 33, "xyz"), (5001, 2, "xy"), (6000, 3, "z"), (8192, 2, "xyz"),
+                                     (10000, 5, "xyz"), (10240, 1, "xyz")])
+def test_fft_fast_path_vs_oracle_and_general_kernel(T, N, dim, monkeypatch):
+    """Every R1 instantiation of the three-pass kernel: against the oracle, and
+    against the general mixed-radix kernel (TA_B200_FFT_GENERAL=1) on the same data."""
+    vel, _ = random_trajectory(T, N, seed=T + N, rho=0.8)
+    u = make_universe(None, vel)
+    cols, _ = oracle.parse_dim_type(dim)
+    v = VACF(u.atoms, dim_type=dim, fft=True).run()
+    plan = v._ctx.fft_plan_info()
+    assert plan["radices"][1:] == [16, 16] and plan["H"] == 256 * plan["radices"][0], plan
+    ref_bp, ref_ts = oracle.vacf_fft(_f64(vel)[:, :, cols])
+    assert_close_normwise(v.results.vacf_by_particle, ref_bp, TOL64, "fast vs oracle, by particle")
+    assert_close_normwise(v.results.timeseries, ref_ts, TOL64, "fast vs oracle, timeseries")
+    monkeypatch.setenv("TA_B200_FFT_GENERAL", "1")
+    g = VACF(u.atoms, dim_type=dim, fft=True).run()
+    assert g._ctx.fft_plan_info()["radices"][1:] != [16, 16]
+    assert_close_normwise(g.results.vacf_by_particle, v.results.vacf_by_particle, 1e-12, "fast vs general kernel")
+
+
+def test_fft_fast_path_ramp_known_answer():
+    """The reference's step trajectory (v = t, 5001 frames) takes the fast path (R1 = 10)."""
+    t = np.arange(5001, dtype=np.float64)
+    v = np.repeat(t[:, None, None], 3, axis=2)
+    u = make_universe(None, v)
+    a = VACF(u.atoms, fft=True).run()
+    assert a._ctx.fft_plan_info()["radices"] == [10, 16, 16]
+    poly = oracle.characteristic_poly(5001, 3)
+    assert_almost_equal(a.results.timeseries, poly, decimal=3)     # the reference's own bar (tests :454-469)
+    assert_close_normwise(a.results.timeseries, poly, TOL64)
+
+
 # ------------------------------------------------------------------ size-independent properties at BASELINE sizes
 def test_properties_at_config_sizes():
     """Config 1 size (1,000 x 5,000): the oracle is too slow for the full set,

@@ -1,0 +1,340 @@
+// K1 fast path: FFT autocorrelation with H = 256 * R1 in three passes.
+//
+// Same mathematics as the general kernel (fft_plan.h / fft_core.cuh; replaces
+// tidynamics.acf as called from transport_analysis/velocityautocorr.py:210-214):
+// the real series is packed z[n] = x[2n] + i x[2n+1], the two residue chains
+// r = 0, 1 of the zero-padded length-2H spectrum are H-point complex FFTs, the
+// power spectrum of the real series is formed from conjugate bin pairs and
+// summed over the D series before ONE inverse per residue.
+//
+// What is different is the data movement (the general kernel makes ~12 shared-
+// memory transfers of the H-point buffer per FFT and was bound by them):
+//   * H = R1 * 16 * 16, decimation in frequency, three passes per FFT:
+//       P1  radix R1, stride 256   fused with the global load and the residue twist
+//       P2  radix 16, stride 16    shared -> registers -> shared
+//       P3  radix 16, stride 1     shared -> registers, fused with the pair accumulation
+//     and the mirror image P3' P2' P1' for the inverse, P3' fed from registers,
+//     P1' fused with the final twist / normalisation / store: 2 shared-memory
+//     round trips per FFT.
+//   * In P3 the thread -> butterfly map puts conjugate-partner butterflies on
+//     lanes l and l ^ 16, so partner bins are exchanged with shuffles and the
+//     (Sigma, Delta) accumulators of a thread's 8 bin pairs stay in registers
+//     over the D series; the same exchange feeds the inverse.
+//   * All butterflies are register DFTs with compile-time constants
+//     (dft_regs.cuh); P2 twiddles come from a 240-entry table, P1 twiddles are
+//     powers of one table entry per thread.
+//   * Shared buffer layout: element e lives at e + (e >> 4) (one pad element
+//     per 16), which makes all three access patterns bank-conflict free.
+#pragma once
+#include <cstdint>
+#include <vector>
+#include "ta_common.cuh"
+#include "dft_regs.cuh"
+#include "fft_plan.h"
+
+namespace ta {
+
+struct K1FArgs {
+    const double* series;        // [natoms][D][Tld]
+    double* by_particle;         // [natoms][Tld]
+    double* partial;             // [grid][Tld]
+    const cd* omega;             // [256]      w_{2H}^j
+    const cd* tw2;               // [15][16]   w_256^{j k}, k = 1..15
+    const uint32_t* map;         // [2][16 R1] P3 butterfly of a thread, per residue (+ flags)
+    const cd* wbase;             // [2][16 R1] w_L^{2 G0 + r} of that butterfly
+    const double* inv;           // [Tld]      1 / (L (T - k)), 0 beyond T
+    int natoms, D, T, nh;
+    long long Tld;
+};
+
+constexpr uint32_t K1F_SELF0 = 1u << 30;   // butterfly holding g = 0 (pairs k <-> 16-k in-thread)
+constexpr uint32_t K1F_SELF8 = 1u << 31;   // butterfly holding g = H/2 (pairs k <-> 15-k in-thread)
+
+constexpr int k1f_smem_bytes(int R1) { return (256 * R1 + 16 * R1 + 256 + 240) * (int)sizeof(cd); }
+// resident CTAs per SM the kernel is compiled for (register budget ~200 / thread, <= 384 threads / SM)
+constexpr int k1f_min_blocks(int R1) { return 384 / (16 * R1) < 1 ? 1 : 384 / (16 * R1); }
+
+// ---------------------------------------------------------------------------
+// P1 twiddles: tw[k] = om^(2k + r), k < R1, from om = w_{2H}^j, two-level.
+// ---------------------------------------------------------------------------
+template <int R1>
+TA_HD void k1f_p1_twiddles(cd om, int r, cd* e, cd* g) {
+    // e[b] = om^(2b + r), b < 4 ; g[a] = om^(8a), a < ceil(R1/4)
+    cd w2 = cmul(om, om), w4 = cmul(w2, w2), w6 = cmul(w4, w2), w8 = cmul(w4, w4);
+    if (r) {
+        e[0] = om; e[1] = cmul(w2, om); e[2] = cmul(w4, om); e[3] = cmul(w6, om);
+    } else {
+        e[0] = cmake<double>(1.0, 0.0); e[1] = w2; e[2] = w4; e[3] = w6;
+    }
+    constexpr int NG = (R1 + 3) / 4;
+    g[0] = cmake<double>(1.0, 0.0);
+    if (NG > 1) g[1] = w8;
+    if (NG > 2) g[2] = cmul(w8, w8);
+    if (NG > 3) g[3] = cmul(g[2], w8);
+    if (NG > 4) g[4] = cmul(g[2], g[2]);
+    if (NG > 5) g[5] = cmul(g[4], w8);
+}
+
+// ---------------------------------------------------------------------------
+// The kernel body for one CTA.  Ctx supplies sync() and shfl_xor16(); on the
+// device these are __syncthreads / __shfl_xor_sync, in tests/emu they are
+// cooperative-fiber versions so the very same code runs on the CPU.
+// ---------------------------------------------------------------------------
+template <int R1, class Ctx>
+TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid, int nblk) {
+    constexpr int H = 256 * R1;
+    constexpr int NT = 16 * R1;
+    constexpr int NG = (R1 + 3) / 4;
+    cd* buf = reinterpret_cast<cd*>(smem_raw);       // H + H/16 elements, padded layout
+    cd* s_om = buf + (H + H / 16);                   // 256
+    cd* s_tw2 = s_om + 256;                          // 240
+
+    for (int i = tid; i < 256; i += NT) s_om[i] = A.omega[i];
+    for (int i = tid; i < 240; i += NT) s_tw2[i] = A.tw2[i];
+    const uint32_t map0 = A.map[tid], map1 = A.map[NT + tid];
+    const cd wb0 = A.wbase[tid], wb1 = A.wbase[NT + tid];
+    Ctx::sync();
+
+    const int nh = A.nh;
+    const int p2base = (tid >> 4) * 272 + (tid & 15);   // P2: padded address of (blk*256 + j), + 17 q
+    const int j2 = tid & 15;
+    cd* part = reinterpret_cast<cd*>(A.partial + (size_t)bid * A.Tld);
+    const cd* inv2 = reinterpret_cast<const cd*>(A.inv);
+
+    for (int atom = bid; atom < A.natoms; atom += nblk) {
+        const double* ser = A.series + (size_t)atom * A.D * A.Tld;
+        cd* row = reinterpret_cast<cd*>(A.by_particle + (size_t)atom * A.Tld);
+        for (int r = 0; r < 2; ++r) {
+            const uint32_t mp = r ? map1 : map0;
+            const cd wb = r ? wb1 : wb0;
+            const int p3base = (int)(mp & 0xffffu) * 17;
+            const bool self0 = (mp & K1F_SELF0) != 0, self8 = (mp & K1F_SELF8) != 0;
+            double acc_s[8], acc_d[8], acc8 = 0.0;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) { acc_s[m] = 0.0; acc_d[m] = 0.0; }
+
+            for (int d = 0; d < A.D; ++d) {
+                // ---------------- P1: global -> registers -> shared
+                const cd* src = reinterpret_cast<const cd*>(ser + (size_t)d * A.Tld);
+                for (int j = tid; j < 256; j += NT) {
+                    cd x[R1];
+#pragma unroll
+                    for (int q = 0; q < R1; ++q) {
+                        const int n = j + 256 * q;
+                        x[q] = (n < nh) ? src[n] : cmake<double>(0.0, 0.0);
+                    }
+                    if (r) {
+                        static_for<1, R1>([&](auto iq) {
+                            constexpr int q = decltype(iq)::value;
+                            x[q] = mul_tw<q, 2 * R1, -1>(x[q]);
+                        });
+                    }
+                    Dft<R1, -1>::run(x);
+                    cd e[4], g[NG];
+                    k1f_p1_twiddles<R1>(s_om[j], r, e, g);
+                    cd* dst = buf + j + (j >> 4);
+#pragma unroll
+                    for (int k = 0; k < R1; ++k) {
+                        cd y = x[k];
+                        if (k >= 4) y = cmul(y, g[k >> 2]);
+                        if (r || (k & 3)) y = cmul(y, e[k & 3]);
+                        dst[272 * k] = y;
+                    }
+                }
+                Ctx::sync();
+                // ---------------- P2: radix 16, stride 16
+                {
+                    cd x[16];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) x[q] = buf[p2base + 17 * q];
+                    Dft<16, -1>::run(x);
+                    buf[p2base] = x[0];
+#pragma unroll
+                    for (int k = 1; k < 16; ++k) buf[p2base + 17 * k] = cmul(x[k], s_tw2[(k - 1) * 16 + j2]);
+                }
+                Ctx::sync();
+                // ---------------- P3: radix 16, stride 1, + pair accumulation
+                {
+                    cd v[16];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) v[q] = buf[p3base + q];
+                    Dft<16, -1>::run(v);
+                    static_for<0, 8>([&](auto im) {
+                        constexpr int m = decltype(im)::value;
+                        cd snd = v[15 - m], rec;
+                        rec.x = Ctx::shfl_xor16(snd.x);
+                        rec.y = Ctx::shfl_xor16(snd.y);
+                        if (self8) rec = snd;
+                        if (self0) rec = v[(16 - m) & 15];
+                        const cd w = mul_tw<m, 32, -1>(wb);
+                        const cd U = v[m];
+                        const double nu = cnorm2(U), nv = cnorm2(rec);
+                        const double B = U.x * rec.y + U.y * rec.x;
+                        acc_s[m] += nu + nv;
+                        acc_d[m] += 2.0 * w.x * B + w.y * (nu - nv);
+                    });
+                    if (self0) acc8 += 2.0 * cnorm2(v[8]);
+                }
+                if (d + 1 < A.D) Ctx::sync();   // P1 of the next series overwrites the buffer
+            }
+
+            // ---------------- inverse: build from the accumulators, P3'
+            {
+                cd v[16], ap[8], rc[8];
+                static_for<0, 8>([&](auto im) {
+                    constexpr int m = decltype(im)::value;
+                    const cd w = mul_tw<m, 32, -1>(wb);
+                    const double sig = acc_s[m], del = acc_d[m];
+                    v[m] = cmake<double>(sig + w.y * del, w.x * del);
+                    ap[m] = cmake<double>(sig - w.y * del, w.x * del);
+                    rc[m].x = Ctx::shfl_xor16(ap[m].x);
+                    rc[m].y = Ctx::shfl_xor16(ap[m].y);
+                });
+                static_for<8, 16>([&](auto ii) {
+                    constexpr int idx = decltype(ii)::value;
+                    cd val = rc[15 - idx];
+                    if (self8) val = ap[15 - idx];
+                    if (self0) val = (idx == 8) ? cmake<double>(acc8, 0.0) : ap[16 - idx];
+                    v[idx] = val;
+                });
+                Dft<16, +1>::run(v);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) buf[p3base + q] = v[q];
+            }
+            Ctx::sync();
+            // ---------------- P2'
+            {
+                cd x[16];
+                x[0] = buf[p2base];
+#pragma unroll
+                for (int k = 1; k < 16; ++k) x[k] = cmulc(buf[p2base + 17 * k], s_tw2[(k - 1) * 16 + j2]);
+                Dft<16, +1>::run(x);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) buf[p2base + 17 * q] = x[q];
+            }
+            Ctx::sync();
+            // ---------------- P1' + output
+            for (int j = tid; j < 256; j += NT) {
+                cd e[4], g[NG];
+                k1f_p1_twiddles<R1>(s_om[j], r, e, g);
+                const cd* srcb = buf + j + (j >> 4);
+                cd x[R1];
+#pragma unroll
+                for (int k = 0; k < R1; ++k) {
+                    cd y = srcb[272 * k];
+                    if (k >= 4) y = cmulc(y, g[k >> 2]);
+                    if (r || (k & 3)) y = cmulc(y, e[k & 3]);
+                    x[k] = y;
+                }
+                Dft<R1, +1>::run(x);
+                if (r) {
+                    static_for<1, R1>([&](auto iq) {
+                        constexpr int q = decltype(iq)::value;
+                        x[q] = mul_tw<q, 2 * R1, +1>(x[q]);
+                    });
+                }
+                // x[q] = V_r[n] (r = 1: already multiplied by conj(w_L^{2n})), n = j + 256 q
+                if (r == 0) {
+#pragma unroll
+                    for (int q = 0; q < R1; ++q) {
+                        const int n = j + 256 * q;
+                        if (n < nh) row[n] = x[q];           // parked raw; finished by residue 1
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < R1; ++q) {
+                        const int n = j + 256 * q;
+                        if (n < nh) {
+                            const cd a = row[n], sc = inv2[n], ps = part[n];
+                            const cd o = cmake<double>((a.x + x[q].x) * sc.x, (a.y + x[q].y) * sc.y);
+                            row[n] = o;
+                            part[n] = cmake<double>(ps.x + o.x, ps.y + o.y);
+                        }
+                    }
+                }
+            }
+            // no barrier here: P1 of the next chain writes exactly the elements this
+            // thread has just read in P1'
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Host-side plan for the fast path.
+// ---------------------------------------------------------------------------
+struct K1FastPlan {
+    int R1 = 0, H = 0, L = 0, NT = 0, nh = 0;
+    std::vector<double> omega;    // 256 x (re, im)
+    std::vector<double> tw2;      // 240 x (re, im)
+    std::vector<uint32_t> map;    // 2 x NT
+    std::vector<double> wbase;    // 2 x NT x (re, im)
+    std::vector<double> inv;      // Tld
+};
+
+// radices R1 the library instantiates (even: the lane exchange needs whole warps)
+inline const int* k1f_supported_r1(int* n) {
+    static const int r1s[] = {4, 6, 8, 10, 12, 16, 20};
+    *n = (int)(sizeof(r1s) / sizeof(r1s[0]));
+    return r1s;
+}
+
+// R1 for a series of T frames, or 0 when the general kernel should be used
+// (tiny problems, > 34 % padding, or longer than the largest instantiation).
+inline int k1f_choose_r1(int64_t T) {
+    const int64_t nh = (T + 1) / 2;
+    int n;
+    const int* r1s = k1f_supported_r1(&n);
+    for (int i = 0; i < n; ++i) {
+        const int64_t H = 256 * (int64_t)r1s[i];
+        if (H >= nh) return (3 * H <= 4 * nh + 3) ? r1s[i] : 0;
+    }
+    return 0;
+}
+
+inline int k1f_build_plan(int64_t T, int64_t Tld, int R1, K1FastPlan* p) {
+    if (R1 < 2 || (R1 & 1) || T < 1 || (T + 1) / 2 > 256 * (int64_t)R1) return TA_ERR_INVALID;
+    p->R1 = R1; p->H = 256 * R1; p->L = 4 * p->H; p->NT = 16 * R1; p->nh = (int)((T + 1) / 2);
+    const int64_t L = p->L;
+    p->omega.resize(2 * 256);
+    for (int j = 0; j < 256; ++j) ta_twiddle(2 * j, L, &p->omega[2 * j], &p->omega[2 * j + 1]);   // w_{2H}^j = w_L^{2j}
+    p->tw2.resize(2 * 240);
+    for (int k = 1; k < 16; ++k)
+        for (int j = 0; j < 16; ++j)
+            ta_twiddle((int64_t)j * k, 256, &p->tw2[2 * ((k - 1) * 16 + j)], &p->tw2[2 * ((k - 1) * 16 + j) + 1]);
+    const int NT = p->NT;
+    p->map.assign(2 * (size_t)NT, 0);
+    p->wbase.assign(4 * (size_t)NT, 0.0);
+    // residue 0: owner / partner butterflies (see DESIGN.md "K1 fast path")
+    std::vector<uint32_t> own(8 * R1), par(8 * R1);
+    int pi = 0;
+    for (int k2 = 0; k2 < 8; ++k2, ++pi) {
+        own[pi] = (uint32_t)k2 | (k2 == 0 ? K1F_SELF0 : 0u);
+        par[pi] = (k2 == 0) ? (8u | K1F_SELF8) : (uint32_t)(16 - k2);
+    }
+    for (int k1 = 1; k1 < R1 / 2; ++k1)
+        for (int k2 = 0; k2 < 16; ++k2, ++pi) {
+            own[pi] = (uint32_t)(k1 * 16 + k2);
+            par[pi] = (uint32_t)((R1 - k1) * 16 + 15 - k2);
+        }
+    for (int k2 = 0; k2 < 8; ++k2, ++pi) {
+        own[pi] = (uint32_t)((R1 / 2) * 16 + k2);
+        par[pi] = (uint32_t)((R1 / 2) * 16 + 15 - k2);
+    }
+    if (pi != 8 * R1) return TA_ERR_INVALID;
+    for (int tid = 0; tid < NT; ++tid) {
+        const int w = tid >> 5, l = tid & 31, pidx = w * 16 + (l & 15), side = l >> 4;
+        p->map[tid] = side ? par[pidx] : own[pidx];
+        p->map[NT + tid] = (uint32_t)(side ? (NT - 1 - pidx) : pidx);
+        for (int r = 0; r < 2; ++r) {
+            const int blk3 = (int)(p->map[r * NT + tid] & 0xffffu);
+            const int k1 = blk3 >> 4, k2 = blk3 & 15;
+            const int64_t G0 = k1 + (int64_t)R1 * k2;
+            ta_twiddle(2 * G0 + r, L, &p->wbase[2 * (r * NT + tid)], &p->wbase[2 * (r * NT + tid) + 1]);
+        }
+    }
+    p->inv.assign((size_t)Tld, 0.0);
+    for (int64_t k = 0; k < T; ++k) p->inv[k] = 1.0 / ((double)L * (double)(T - k));
+    return TA_OK;
+}
+
+}  // namespace ta

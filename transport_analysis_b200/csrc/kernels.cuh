@@ -8,6 +8,7 @@
 #include "ta_common.cuh"
 #include "fft_core.cuh"
 #include "windowed_core.cuh"
+#include "k1_fast.cuh"
 
 namespace ta {
 
@@ -121,6 +122,31 @@ k1_fft_acf(const K1Args<R> args) {
             __syncthreads();
         }
     }
+}
+
+// ---------------------------------------------------------------------------
+// K1 fast path (k1_fast.cuh): H = 256 R1 in three register-DFT passes.
+// ---------------------------------------------------------------------------
+struct DevCtx {
+    static TA_HD void sync() {
+#if defined(__CUDA_ARCH__)
+        __syncthreads();
+#endif
+    }
+    static TA_HD double shfl_xor16(double v) {
+#if defined(__CUDA_ARCH__)
+        return __shfl_xor_sync(0xffffffffu, v, 16);
+#else
+        return v;
+#endif
+    }
+};
+
+template <int R1>
+__global__ void __launch_bounds__(16 * R1, k1f_min_blocks(R1))
+k1f_fft_acf(const K1FArgs args) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    k1f_body<R1, DevCtx>(args, smem_raw, (int)threadIdx.x, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // ---------------------------------------------------------------------------

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -99,6 +100,12 @@ struct Shard {
     uint32_t* ftab = nullptr;
     uint32_t* pair0 = nullptr;
     uint32_t* own0 = nullptr;
+    // fast-path FFT tables (k1_fast.cuh)
+    void* f_omega = nullptr;
+    void* f_tw2 = nullptr;
+    uint32_t* f_map = nullptr;
+    void* f_wbase = nullptr;
+    double* f_inv = nullptr;
 };
 
 }  // namespace
@@ -126,6 +133,7 @@ struct ta_ctx {
     int64_t plan_T = -1;
     int plan_prec = -1;
     int npairs0 = 0;
+    int fast_r1 = 0;         // > 0: the plan is for the fast path with this R1
     int k1_threads = 0, k1_smem = 0, k1_grid = 0;
     std::vector<double> host_ts;
     int64_t launches = 0;
@@ -170,6 +178,11 @@ void free_problem(ta_ctx* c) {
         cudaFree(s.ftab); s.ftab = nullptr;
         cudaFree(s.pair0); s.pair0 = nullptr;
         cudaFree(s.own0); s.own0 = nullptr;
+        cudaFree(s.f_omega); s.f_omega = nullptr;
+        cudaFree(s.f_tw2); s.f_tw2 = nullptr;
+        cudaFree(s.f_map); s.f_map = nullptr;
+        cudaFree(s.f_wbase); s.f_wbase = nullptr;
+        cudaFree(s.f_inv); s.f_inv = nullptr;
     }
     for (int i = 0; i < kNumSlabs; ++i) {
         if (c->slab[i]) cudaFreeHost(c->slab[i]);
@@ -346,8 +359,42 @@ int upload_fft_tables(ta_ctx* ctx, const std::vector<uint32_t>& own0) {
     return TA_OK;
 }
 
+int upload_fast_tables(ta_ctx* ctx, const K1FastPlan& p) {
+    for (auto& s : ctx->sh) {
+        CK(cudaSetDevice(s.dev));
+        cudaFree(s.f_omega); cudaFree(s.f_tw2); cudaFree(s.f_map); cudaFree(s.f_wbase); cudaFree(s.f_inv);
+        s.f_omega = s.f_tw2 = s.f_wbase = nullptr; s.f_map = nullptr; s.f_inv = nullptr;
+#define TA_UP(dst, vec)                                                                         \
+        CK(cudaMalloc((void**)&dst, vec.size() * sizeof(vec[0])));                              \
+        CK(cudaMemcpy(dst, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice));
+        TA_UP(s.f_omega, p.omega);
+        TA_UP(s.f_tw2, p.tw2);
+        TA_UP(s.f_map, p.map);
+        TA_UP(s.f_wbase, p.wbase);
+        TA_UP(s.f_inv, p.inv);
+#undef TA_UP
+    }
+    return TA_OK;
+}
+
 int ensure_fft_plan(ta_ctx* ctx) {
     if (ctx->plan_T == ctx->T && ctx->plan_prec == ctx->precision) return TA_OK;
+    ctx->fast_r1 = 0;
+    const char* force_general = getenv("TA_B200_FFT_GENERAL");
+    const int r1 = (ctx->precision == TA_PRECISION_FP64 && !(force_general && force_general[0] == '1'))
+                       ? k1f_choose_r1(ctx->T) : 0;
+    if (r1 > 0) {
+        K1FastPlan fp;
+        int rcf = k1f_build_plan(ctx->T, ctx->Tld, r1, &fp);
+        if (rcf) return fail(ctx, rcf, "cannot plan the fast FFT path for T=" + std::to_string(ctx->T));
+        if ((rcf = upload_fast_tables(ctx, fp))) return rcf;
+        ctx->fast_r1 = r1;
+        ctx->plan.H = fp.H; ctx->plan.L = fp.L; ctx->plan.npasses = 3;
+        ctx->plan.radix[0] = r1; ctx->plan.radix[1] = 16; ctx->plan.radix[2] = 16;
+        ctx->plan_T = ctx->T;
+        ctx->plan_prec = ctx->precision;
+        return TA_OK;
+    }
     int rc = ta_build_fft_plan(ctx->T, &ctx->plan);
     if (rc) return fail(ctx, rc, "cannot plan an FFT for T=" + std::to_string(ctx->T));
     std::vector<uint32_t> own0;
@@ -408,6 +455,52 @@ int launch_fft(ta_ctx* ctx, std::vector<int>* grids) {
         ctx->k1_threads = nthr; ctx->k1_smem = (int)smem; ctx->k1_grid = grid;
     }
     return TA_OK;
+}
+
+template <int R1>
+int launch_fft_fast_r1(ta_ctx* ctx, std::vector<int>* grids) {
+    const int smem = k1f_smem_bytes(R1);
+    const int nthr = 16 * R1;
+    grids->assign(ctx->sh.size(), 0);
+    for (size_t i = 0; i < ctx->sh.size(); ++i) {
+        Shard& s = ctx->sh[i];
+        if (s.natoms == 0) continue;
+        CK(cudaSetDevice(s.dev));
+        CK(cudaFuncSetAttribute(k1f_fft_acf<R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1f_fft_acf<R1>, nthr, (size_t)smem));
+        if (occ < 1) return fail(ctx, TA_ERR_UNSUPPORTED, "fast FFT kernel does not fit on an SM");
+        int grid = (int)std::min<int64_t>(s.natoms, (int64_t)s.num_sms * occ);
+        (*grids)[i] = grid;
+        int rc = ensure_partial(ctx, s, (size_t)grid);
+        if (rc) return rc;
+        K1FArgs a;
+        a.series = s.series; a.by_particle = s.by_particle; a.partial = s.partial;
+        a.omega = (const cd*)s.f_omega; a.tw2 = (const cd*)s.f_tw2; a.map = s.f_map;
+        a.wbase = (const cd*)s.f_wbase; a.inv = s.f_inv;
+        a.natoms = (int)s.natoms; a.D = ctx->D; a.T = (int)ctx->T; a.nh = (int)((ctx->T + 1) / 2); a.Tld = ctx->Tld;
+        CK(cudaEventRecord(s.ev_ka, s.s_compute));
+        k1f_fft_acf<R1><<<grid, nthr, smem, s.s_compute>>>(a);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(s.ev_kb, s.s_compute));
+        s.kernel_timed = true;
+        ctx->launches++;
+        ctx->k1_threads = nthr; ctx->k1_smem = smem; ctx->k1_grid = grid;
+    }
+    return TA_OK;
+}
+
+int launch_fft_fast(ta_ctx* ctx, std::vector<int>* grids) {
+    switch (ctx->fast_r1) {
+        case 4: return launch_fft_fast_r1<4>(ctx, grids);
+        case 6: return launch_fft_fast_r1<6>(ctx, grids);
+        case 8: return launch_fft_fast_r1<8>(ctx, grids);
+        case 10: return launch_fft_fast_r1<10>(ctx, grids);
+        case 12: return launch_fft_fast_r1<12>(ctx, grids);
+        case 16: return launch_fft_fast_r1<16>(ctx, grids);
+        case 20: return launch_fft_fast_r1<20>(ctx, grids);
+    }
+    return fail(ctx, TA_ERR_UNSUPPORTED, "no fast FFT instantiation for R1=" + std::to_string(ctx->fast_r1));
 }
 
 template <typename R, int MODE>
@@ -746,7 +839,8 @@ int ta_vacf_fft(ta_ctx* ctx, double* ts_out) {
     if (!ts_out) return fail(ctx, TA_ERR_INVALID, "ts_out is null");
     if ((rc = ensure_fft_plan(ctx))) return rc;
     std::vector<int> grids;
-    rc = (ctx->precision == TA_PRECISION_FP64) ? launch_fft<double>(ctx, &grids) : launch_fft<float>(ctx, &grids);
+    if (ctx->fast_r1 > 0) rc = launch_fft_fast(ctx, &grids);
+    else rc = (ctx->precision == TA_PRECISION_FP64) ? launch_fft<double>(ctx, &grids) : launch_fft<float>(ctx, &grids);
     if (rc) return rc;
     return finish_timeseries(ctx, grids, ts_out);
 }
