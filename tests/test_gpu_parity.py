@@ -247,7 +247,7 @@ def test_fft_fast_path_vs_oracle_and_general_kernel(T, N, dim, monkeypatch):
     monkeypatch.setenv("TA_B200_FFT_GENERAL", "1")
     g = VACF(u.atoms, dim_type=dim, fft=True).run()
     assert g._ctx.fft_plan_info()["radices"][1:] != [16, 16]
-    assert_close_normwise(g.results.vacf_by_particle, v.results.vacf_by_particle, 1e-12, "fast vs general kernel")
+    assert_close_normwise(g.results.vacf_by_particle, v.results.vacf_by_particle, 1e-11, "fast vs general kernel")
 
 
 def test_fft_fast_path_ramp_known_answer():

@@ -45,14 +45,20 @@ struct K1FArgs {
     const double* inv;           // [Tld]      1 / (L (T - k)), 0 beyond T
     int natoms, D, T, nh;
     long long Tld;
+    long long* prof;             // optional [grid][12] per-phase clock totals of thread 0 (debug; may be null)
+    int prefetch;                // 1: ask L2 for the next particle's series at the start of each particle
 };
 
 constexpr uint32_t K1F_SELF0 = 1u << 30;   // butterfly holding g = 0 (pairs k <-> 16-k in-thread)
 constexpr uint32_t K1F_SELF8 = 1u << 31;   // butterfly holding g = H/2 (pairs k <-> 15-k in-thread)
 
 constexpr int k1f_smem_bytes(int R1) { return (256 * R1 + 16 * R1 + 256 + 240) * (int)sizeof(cd); }
-// resident CTAs per SM the kernel is compiled for (register budget ~200 / thread, <= 384 threads / SM)
-constexpr int k1f_min_blocks(int R1) { return 384 / (16 * R1) < 1 ? 1 : 384 / (16 * R1); }
+// radix-16 butterflies per thread (NB) and resident CTAs per SM the kernel is compiled for:
+// CTAs of 64..192 threads, <= 320 threads per SM so that every thread may hold ~200 registers,
+// and at least two CTAs per SM so that one CTA's barriers and load latency overlap the other's math.
+constexpr int k1f_nb(int R1) { return R1 >= 12 ? 2 : 1; }
+constexpr int k1f_threads(int R1, int NB) { return 16 * R1 / NB; }
+constexpr int k1f_min_blocks(int R1, int NB) { return 320 / k1f_threads(R1, NB) < 1 ? 1 : 320 / k1f_threads(R1, NB); }
 
 // ---------------------------------------------------------------------------
 // P1 twiddles: tw[k] = om^(2k + r), k < R1, from om = w_{2H}^j, two-level.
@@ -80,38 +86,45 @@ TA_HD void k1f_p1_twiddles(cd om, int r, cd* e, cd* g) {
 // device these are __syncthreads / __shfl_xor_sync, in tests/emu they are
 // cooperative-fiber versions so the very same code runs on the CPU.
 // ---------------------------------------------------------------------------
-template <int R1, class Ctx>
+template <int R1, int NB, class Ctx, bool PROF = false>
 TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid, int nblk) {
     constexpr int H = 256 * R1;
-    constexpr int NT = 16 * R1;
+    constexpr int NV = 16 * R1;          // radix-16 butterflies per pass ("virtual threads")
+    constexpr int NT = NV / NB;          // threads per CTA; each owns NB butterflies of P2 / P3
     constexpr int NG = (R1 + 3) / 4;
+    static_assert(NV % NB == 0 && NT % 32 == 0, "the lane exchange needs whole warps");
     cd* buf = reinterpret_cast<cd*>(smem_raw);       // H + H/16 elements, padded layout
     cd* s_om = buf + (H + H / 16);                   // 256
     cd* s_tw2 = s_om + 256;                          // 240
 
     for (int i = tid; i < 256; i += NT) s_om[i] = A.omega[i];
     for (int i = tid; i < 240; i += NT) s_tw2[i] = A.tw2[i];
-    const uint32_t map0 = A.map[tid], map1 = A.map[NT + tid];
-    const cd wb0 = A.wbase[tid], wb1 = A.wbase[NT + tid];
     Ctx::sync();
 
     const int nh = A.nh;
-    const int p2base = (tid >> 4) * 272 + (tid & 15);   // P2: padded address of (blk*256 + j), + 17 q
-    const int j2 = tid & 15;
+    const int j2 = tid & 15;                         // NT is a multiple of 16: the same for every owned butterfly
     cd* part = reinterpret_cast<cd*>(A.partial + (size_t)bid * A.Tld);
     const cd* inv2 = reinterpret_cast<const cd*>(A.inv);
+
+    long long tprev = 0;
+    long long* prof = (PROF && A.prof != nullptr && tid == 0) ? A.prof + 32 * (size_t)bid : nullptr;
+    if (PROF && prof) tprev = Ctx::clock();
+    // debug instrumentation (PROF instantiation only): clocks of thread 0 between phase boundaries;
+    // `dep` makes the clock read wait for a value (e.g. the last load of a batch)
+#define K1F_TICK(ph, dep) do { if (PROF && prof) { const long long tn_ = Ctx::clock_after(dep); prof[r * 16 + (ph)] += tn_ - tprev; tprev = tn_; } } while (0)
 
     for (int atom = bid; atom < A.natoms; atom += nblk) {
         const double* ser = A.series + (size_t)atom * A.D * A.Tld;
         cd* row = reinterpret_cast<cd*>(A.by_particle + (size_t)atom * A.Tld);
+        if (A.prefetch && atom + nblk < A.natoms) Ctx::prefetch_l2(ser + (size_t)nblk * A.D * A.Tld, A.D * A.Tld * sizeof(double), tid, NT);
         for (int r = 0; r < 2; ++r) {
-            const uint32_t mp = r ? map1 : map0;
-            const cd wb = r ? wb1 : wb0;
-            const int p3base = (int)(mp & 0xffffu) * 17;
-            const bool self0 = (mp & K1F_SELF0) != 0, self8 = (mp & K1F_SELF8) != 0;
-            double acc_s[8], acc_d[8], acc8 = 0.0;
+            double acc_s[NB][8], acc_d[NB][8], acc8[NB];
 #pragma unroll
-            for (int m = 0; m < 8; ++m) { acc_s[m] = 0.0; acc_d[m] = 0.0; }
+            for (int it = 0; it < NB; ++it) {
+                acc8[it] = 0.0;
+#pragma unroll
+                for (int m = 0; m < 8; ++m) { acc_s[it][m] = 0.0; acc_d[it][m] = 0.0; }
+            }
 
             for (int d = 0; d < A.D; ++d) {
                 // ---------------- P1: global -> registers -> shared
@@ -121,8 +134,9 @@ TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid,
 #pragma unroll
                     for (int q = 0; q < R1; ++q) {
                         const int n = j + 256 * q;
-                        x[q] = (n < nh) ? src[n] : cmake<double>(0.0, 0.0);
+                        x[q] = (n < nh) ? Ctx::ld_stream(src + n) : cmake<double>(0.0, 0.0);
                     }
+                    K1F_TICK(0, x[R1 - 1].y + x[0].x);
                     if (r) {
                         static_for<1, R1>([&](auto iq) {
                             constexpr int q = decltype(iq)::value;
@@ -138,26 +152,44 @@ TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid,
                         cd y = x[k];
                         if (k >= 4) y = cmul(y, g[k >> 2]);
                         if (r || (k & 3)) y = cmul(y, e[k & 3]);
-                        dst[272 * k] = y;
+                        x[k] = y;
                     }
+                    K1F_TICK(1, x[R1 - 1].y + x[1].x);
+#pragma unroll
+                    for (int k = 0; k < R1; ++k) dst[272 * k] = x[k];
                 }
                 Ctx::sync();
+                K1F_TICK(2, 0.0);
                 // ---------------- P2: radix 16, stride 16
-                {
+#pragma unroll
+                for (int it = 0; it < NB; ++it) {
+                    const int vt = tid + it * NT;
+                    const int p2base = (vt >> 4) * 272 + j2;     // padded address of (blk*256 + j), + 17 q
                     cd x[16];
 #pragma unroll
                     for (int q = 0; q < 16; ++q) x[q] = buf[p2base + 17 * q];
+                    K1F_TICK(3, x[15].y + x[0].x);
                     Dft<16, -1>::run(x);
-                    buf[p2base] = x[0];
 #pragma unroll
-                    for (int k = 1; k < 16; ++k) buf[p2base + 17 * k] = cmul(x[k], s_tw2[(k - 1) * 16 + j2]);
+                    for (int k = 1; k < 16; ++k) x[k] = cmul(x[k], s_tw2[(k - 1) * 16 + j2]);
+                    K1F_TICK(4, x[15].y + x[1].x);
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) buf[p2base + 17 * k] = x[k];
                 }
                 Ctx::sync();
+                K1F_TICK(5, 0.0);
                 // ---------------- P3: radix 16, stride 1, + pair accumulation
-                {
+                static_for<0, NB>([&](auto iit) {
+                    constexpr int it = decltype(iit)::value;
+                    const int vt = tid + it * NT;
+                    const uint32_t mp = A.map[r * NV + vt];
+                    const cd wb = A.wbase[r * NV + vt];
+                    const int p3base = (int)(mp & 0xffffu) * 17;
+                    const bool self0 = (mp & K1F_SELF0) != 0, self8 = (mp & K1F_SELF8) != 0;
                     cd v[16];
 #pragma unroll
                     for (int q = 0; q < 16; ++q) v[q] = buf[p3base + q];
+                    K1F_TICK(6, v[15].y + v[0].x);
                     Dft<16, -1>::run(v);
                     static_for<0, 8>([&](auto im) {
                         constexpr int m = decltype(im)::value;
@@ -170,21 +202,29 @@ TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid,
                         const cd U = v[m];
                         const double nu = cnorm2(U), nv = cnorm2(rec);
                         const double B = U.x * rec.y + U.y * rec.x;
-                        acc_s[m] += nu + nv;
-                        acc_d[m] += 2.0 * w.x * B + w.y * (nu - nv);
+                        acc_s[it][m] += nu + nv;
+                        acc_d[it][m] += 2.0 * w.x * B + w.y * (nu - nv);
                     });
-                    if (self0) acc8 += 2.0 * cnorm2(v[8]);
-                }
+                    if (self0) acc8[it] += 2.0 * cnorm2(v[8]);
+                    K1F_TICK(7, acc_d[it][7] + acc_s[it][0]);
+                });
                 if (d + 1 < A.D) Ctx::sync();   // P1 of the next series overwrites the buffer
+                K1F_TICK(8, 0.0);
             }
 
             // ---------------- inverse: build from the accumulators, P3'
-            {
+            static_for<0, NB>([&](auto iit) {
+                constexpr int it = decltype(iit)::value;
+                const int vt = tid + it * NT;
+                const uint32_t mp = A.map[r * NV + vt];
+                const cd wb = A.wbase[r * NV + vt];
+                const int p3base = (int)(mp & 0xffffu) * 17;
+                const bool self0 = (mp & K1F_SELF0) != 0, self8 = (mp & K1F_SELF8) != 0;
                 cd v[16], ap[8], rc[8];
                 static_for<0, 8>([&](auto im) {
                     constexpr int m = decltype(im)::value;
                     const cd w = mul_tw<m, 32, -1>(wb);
-                    const double sig = acc_s[m], del = acc_d[m];
+                    const double sig = acc_s[it][m], del = acc_d[it][m];
                     v[m] = cmake<double>(sig + w.y * del, w.x * del);
                     ap[m] = cmake<double>(sig - w.y * del, w.x * del);
                     rc[m].x = Ctx::shfl_xor16(ap[m].x);
@@ -194,25 +234,32 @@ TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid,
                     constexpr int idx = decltype(ii)::value;
                     cd val = rc[15 - idx];
                     if (self8) val = ap[15 - idx];
-                    if (self0) val = (idx == 8) ? cmake<double>(acc8, 0.0) : ap[16 - idx];
+                    if (self0) val = (idx == 8) ? cmake<double>(acc8[it], 0.0) : ap[16 - idx];
                     v[idx] = val;
                 });
                 Dft<16, +1>::run(v);
+                K1F_TICK(9, v[15].y + v[0].x);
 #pragma unroll
                 for (int q = 0; q < 16; ++q) buf[p3base + q] = v[q];
-            }
+            });
             Ctx::sync();
+            K1F_TICK(10, 0.0);
             // ---------------- P2'
-            {
+#pragma unroll
+            for (int it = 0; it < NB; ++it) {
+                const int vt = tid + it * NT;
+                const int p2base = (vt >> 4) * 272 + j2;
                 cd x[16];
                 x[0] = buf[p2base];
 #pragma unroll
                 for (int k = 1; k < 16; ++k) x[k] = cmulc(buf[p2base + 17 * k], s_tw2[(k - 1) * 16 + j2]);
                 Dft<16, +1>::run(x);
+                K1F_TICK(11, x[15].y + x[0].x);
 #pragma unroll
                 for (int q = 0; q < 16; ++q) buf[p2base + 17 * q] = x[q];
             }
             Ctx::sync();
+            K1F_TICK(12, 0.0);
             // ---------------- P1' + output
             for (int j = tid; j < 256; j += NT) {
                 cd e[4], g[NG];
@@ -234,6 +281,7 @@ TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid,
                     });
                 }
                 // x[q] = V_r[n] (r = 1: already multiplied by conj(w_L^{2n})), n = j + 256 q
+                K1F_TICK(13, x[R1 - 1].y + x[0].x);
                 if (r == 0) {
 #pragma unroll
                     for (int q = 0; q < R1; ++q) {
@@ -241,22 +289,44 @@ TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid,
                         if (n < nh) row[n] = x[q];           // parked raw; finished by residue 1
                     }
                 } else {
+                    // Park the finished V_1 values in this thread's own buffer slots, then stream the
+                    // output in chunks with all global loads of a chunk issued first: with x[] out of
+                    // the registers there is room to keep a whole chunk of L2 round trips in flight
+                    // (the row / part stores may alias the loads as far as the compiler knows).
+                    cd* own = buf + j + (j >> 4);
 #pragma unroll
-                    for (int q = 0; q < R1; ++q) {
-                        const int n = j + 256 * q;
-                        if (n < nh) {
-                            const cd a = row[n], sc = inv2[n], ps = part[n];
-                            const cd o = cmake<double>((a.x + x[q].x) * sc.x, (a.y + x[q].y) * sc.y);
-                            row[n] = o;
-                            part[n] = cmake<double>(ps.x + o.x, ps.y + o.y);
+                    for (int q = 0; q < R1; ++q) own[272 * q] = x[q];
+                    Ctx::compiler_fence();
+                    constexpr int QB = (R1 % 5 == 0) ? 5 : 4;
+                    static_for<0, (R1 + QB - 1) / QB>([&](auto ic) {
+                        constexpr int q0 = decltype(ic)::value * QB;
+                        constexpr int nq = (R1 - q0) < QB ? (R1 - q0) : QB;
+                        cd a[nq], sc[nq], ps[nq];
+#pragma unroll
+                        for (int i = 0; i < nq; ++i) {
+                            const int n = j + 256 * (q0 + i);
+                            const int nc = n < nh ? n : nh - 1;      // clamped: the loads stay branch-free
+                            a[i] = Ctx::ld_stream(row + nc); sc[i] = inv2[nc]; ps[i] = Ctx::ld_stream(part + nc);
                         }
-                    }
+#pragma unroll
+                        for (int i = 0; i < nq; ++i) {
+                            const int n = j + 256 * (q0 + i);
+                            if (n < nh) {
+                                const cd v1 = own[272 * (q0 + i)];
+                                const cd o = cmake<double>((a[i].x + v1.x) * sc[i].x, (a[i].y + v1.y) * sc[i].y);
+                                row[n] = o;
+                                part[n] = cmake<double>(ps[i].x + o.x, ps[i].y + o.y);
+                            }
+                        }
+                    });
                 }
             }
             // no barrier here: P1 of the next chain writes exactly the elements this
             // thread has just read in P1'
+            K1F_TICK(14, 0.0);
         }
     }
+#undef K1F_TICK
 }
 
 // ---------------------------------------------------------------------------

@@ -140,13 +140,53 @@ struct DevCtx {
         return v;
 #endif
     }
+    // streaming load: through L2 only, so that L1 keeps the tables every particle re-reads
+    static TA_HD cd ld_stream(const cd* p) {
+#if defined(__CUDA_ARCH__)
+        const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+        return cmake<double>(v.x, v.y);
+#else
+        return *p;
+#endif
+    }
+    static TA_HD void compiler_fence() {
+#if defined(__CUDA_ARCH__)
+        asm volatile("" ::: "memory");
+#endif
+    }
+    static TA_HD long long clock_after(double dep) {
+#if defined(__CUDA_ARCH__)
+        long long t;
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "d"(dep) : "memory");
+        return t;
+#else
+        return 0;
+#endif
+    }
+    static TA_HD long long clock() {
+#if defined(__CUDA_ARCH__)
+        return clock64();
+#else
+        return 0;
+#endif
+    }
+    // ask L2 for `bytes` at p (the next particle's series); 4 KB per participating thread
+    static TA_HD void prefetch_l2(const void* p, size_t bytes, int tid, int nthr) {
+#if defined(__CUDA_ARCH__)
+        const char* c = static_cast<const char*>(p);
+        for (size_t off = (size_t)tid * 4096; off < bytes; off += (size_t)nthr * 4096) {
+            const unsigned n = (unsigned)((bytes - off) < 4096 ? (bytes - off) & ~(size_t)15 : 4096);
+            if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(c + off), "r"(n) : "memory");
+        }
+#endif
+    }
 };
 
-template <int R1>
-__global__ void __launch_bounds__(16 * R1, k1f_min_blocks(R1))
+template <int R1, int NB, bool PROF = false>
+__global__ void __launch_bounds__(k1f_threads(R1, NB), k1f_min_blocks(R1, NB))
 k1f_fft_acf(const K1FArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    k1f_body<R1, DevCtx>(args, smem_raw, (int)threadIdx.x, (int)blockIdx.x, (int)gridDim.x);
+    k1f_body<R1, NB, DevCtx, PROF>(args, smem_raw, (int)threadIdx.x, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // ---------------------------------------------------------------------------

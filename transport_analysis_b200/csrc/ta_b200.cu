@@ -457,18 +457,23 @@ int launch_fft(ta_ctx* ctx, std::vector<int>* grids) {
     return TA_OK;
 }
 
-template <int R1>
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && v[0]) ? atoi(v) : dflt;
+}
+
+template <int R1, int NB, bool PROF = false>
 int launch_fft_fast_r1(ta_ctx* ctx, std::vector<int>* grids) {
     const int smem = k1f_smem_bytes(R1);
-    const int nthr = 16 * R1;
+    const int nthr = k1f_threads(R1, NB);
     grids->assign(ctx->sh.size(), 0);
     for (size_t i = 0; i < ctx->sh.size(); ++i) {
         Shard& s = ctx->sh[i];
         if (s.natoms == 0) continue;
         CK(cudaSetDevice(s.dev));
-        CK(cudaFuncSetAttribute(k1f_fft_acf<R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(k1f_fft_acf<R1, NB, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1f_fft_acf<R1>, nthr, (size_t)smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1f_fft_acf<R1, NB, PROF>, nthr, (size_t)smem));
         if (occ < 1) return fail(ctx, TA_ERR_UNSUPPORTED, "fast FFT kernel does not fit on an SM");
         int grid = (int)std::min<int64_t>(s.natoms, (int64_t)s.num_sms * occ);
         (*grids)[i] = grid;
@@ -479,10 +484,33 @@ int launch_fft_fast_r1(ta_ctx* ctx, std::vector<int>* grids) {
         a.omega = (const cd*)s.f_omega; a.tw2 = (const cd*)s.f_tw2; a.map = s.f_map;
         a.wbase = (const cd*)s.f_wbase; a.inv = s.f_inv;
         a.natoms = (int)s.natoms; a.D = ctx->D; a.T = (int)ctx->T; a.nh = (int)((ctx->T + 1) / 2); a.Tld = ctx->Tld;
+        a.prefetch = env_int("TA_B200_K1F_PREFETCH", 0);
+        a.prof = nullptr;
+        const bool profile = PROF;   // debug instantiation: per-phase clocks of thread 0 to stderr
+        if (profile) {
+            CK(cudaMalloc((void**)&a.prof, (size_t)grid * 32 * sizeof(long long)));
+            CK(cudaMemsetAsync(a.prof, 0, (size_t)grid * 32 * sizeof(long long), s.s_compute));
+        }
         CK(cudaEventRecord(s.ev_ka, s.s_compute));
-        k1f_fft_acf<R1><<<grid, nthr, smem, s.s_compute>>>(a);
+        k1f_fft_acf<R1, NB, PROF><<<grid, nthr, smem, s.s_compute>>>(a);
         CK(cudaGetLastError());
         CK(cudaEventRecord(s.ev_kb, s.s_compute));
+        if (profile) {
+            std::vector<long long> h((size_t)grid * 32);
+            CK(cudaStreamSynchronize(s.s_compute));
+            CK(cudaMemcpy(h.data(), a.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+            CK(cudaFree(a.prof));
+            double tot[32] = {0}, all = 0;
+            for (int b = 0; b < grid; ++b) for (int q = 0; q < 32; ++q) { tot[q] += (double)h[(size_t)b * 32 + q]; all += (double)h[(size_t)b * 32 + q]; }
+            const char* nm[16] = {"P1.ld", "P1.fp", "P1.st+bar", "P2.ld", "P2.fp", "P2.st+bar", "P3.ld", "P3.fp", "P3.bar",
+                                  "P3i.fp", "P3i.st+bar", "P2i.ld+fp", "P2i.st+bar", "P1i.ld+fp", "out", "-"};
+            const double atoms_per_cta = (double)s.natoms / grid;
+            fprintf(stderr, "[k1f profile] R1=%d NB=%d grid=%d clocks/CTA=%.0f clocks/atom=%.0f\n", R1, NB, grid, all / grid,
+                    all / grid / atoms_per_cta);
+            for (int q = 0; q < 32; ++q)
+                if (tot[q] > 0) fprintf(stderr, "   r%d.%-11s %5.1f%%  %7.0f clk/atom\n", q / 16, nm[q % 16], 100.0 * tot[q] / all,
+                                        tot[q] / grid / atoms_per_cta);
+        }
         s.kernel_timed = true;
         ctx->launches++;
         ctx->k1_threads = nthr; ctx->k1_smem = smem; ctx->k1_grid = grid;
@@ -492,13 +520,16 @@ int launch_fft_fast_r1(ta_ctx* ctx, std::vector<int>* grids) {
 
 int launch_fft_fast(ta_ctx* ctx, std::vector<int>* grids) {
     switch (ctx->fast_r1) {
-        case 4: return launch_fft_fast_r1<4>(ctx, grids);
-        case 6: return launch_fft_fast_r1<6>(ctx, grids);
-        case 8: return launch_fft_fast_r1<8>(ctx, grids);
-        case 10: return launch_fft_fast_r1<10>(ctx, grids);
-        case 12: return launch_fft_fast_r1<12>(ctx, grids);
-        case 16: return launch_fft_fast_r1<16>(ctx, grids);
-        case 20: return launch_fft_fast_r1<20>(ctx, grids);
+        case 4: return launch_fft_fast_r1<4, 1>(ctx, grids);
+        case 6: return launch_fft_fast_r1<6, 1>(ctx, grids);
+        case 8: return launch_fft_fast_r1<8, 1>(ctx, grids);
+        case 10: return launch_fft_fast_r1<10, 1>(ctx, grids);
+        case 12: return launch_fft_fast_r1<12, 1>(ctx, grids);
+        case 16: return launch_fft_fast_r1<16, 1>(ctx, grids);
+        case 20:
+            if (env_int("TA_B200_K1F_PROFILE", 0)) return launch_fft_fast_r1<20, 1, true>(ctx, grids);
+            return env_int("TA_B200_K1F_NB", 1) == 2 ? launch_fft_fast_r1<20, 2>(ctx, grids)
+                                                     : launch_fft_fast_r1<20, 1>(ctx, grids);
     }
     return fail(ctx, TA_ERR_UNSUPPORTED, "no fast FFT instantiation for R1=" + std::to_string(ctx->fast_r1));
 }
