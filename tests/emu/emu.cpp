@@ -101,11 +101,11 @@ static int run_k1fast(const double* series, int T, int D, int Tld, int natoms, i
     a.map = p.map.data();
     a.wbase = reinterpret_cast<const cd*>(p.wbase.data());
     a.inv = p.inv.data();
-    a.natoms = natoms; a.D = D; a.T = T; a.nh = p.nh; a.Tld = Tld; a.prefetch = 0; a.prof = nullptr;
+    a.natoms = natoms; a.D = D; a.T = T; a.nh = p.nh; a.Tld = Tld; a.prefetch = 0; a.stagger = 0; a.prof = nullptr;
     std::vector<unsigned char> smem(k1f_smem_bytes(R1) + 64);
     unsigned char* sm = smem.data() + (16 - ((uintptr_t)smem.data() & 15)) % 16;
     for (int bid = 0; bid < nblk; ++bid)
-        emu::run_cta(k1f_threads(R1, k1f_nb(R1)), [&](int tid) { k1f_body<R1, k1f_nb(R1), emu::EmuCtx>(a, sm, tid, bid, nblk); });
+        emu::run_cta(k1f_threads(R1), [&](int tid) { k1f_body<R1, k1f_threads(R1), emu::EmuCtx>(a, sm, tid, bid, nblk); });
     return 0;
 }
 

@@ -118,6 +118,7 @@ struct EmuCtx {
     static double shfl_xor16(double v) { return shfl_xor(v, 16); }
     static void prefetch_l2(const void*, size_t, int, int) {}
     static long long clock() { return 0; }
+    static void spin(int) {}
     static long long clock_after(double) { return 0; }
     static void compiler_fence() {}
     template <class V> static V ld_stream(const V* p) { return *p; }

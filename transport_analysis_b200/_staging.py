@@ -140,5 +140,9 @@ class FrameStager:
         self._fill = 0
 
     def finish(self):
+        """Per-frame path: wait for the last slab.  Bulk path: nothing to wait for -- the compute call
+        that follows is queued behind the staging chunk by chunk (H2D of chunk c+1 overlaps the
+        correlation of chunk c) and synchronises at its end."""
         self.flush()
-        self.ctx.stage_end()
+        if not self.bulk_done:
+            self.ctx.stage_end()

@@ -47,18 +47,23 @@ struct K1FArgs {
     long long Tld;
     long long* prof;             // optional [grid][12] per-phase clock totals of thread 0 (debug; may be null)
     int prefetch;                // 1: ask L2 for the next particle's series at the start of each particle
+    int stagger;                 // clocks the second wave of CTAs (bid >= nblk / 2) idles before its first particle
 };
 
 constexpr uint32_t K1F_SELF0 = 1u << 30;   // butterfly holding g = 0 (pairs k <-> 16-k in-thread)
 constexpr uint32_t K1F_SELF8 = 1u << 31;   // butterfly holding g = H/2 (pairs k <-> 15-k in-thread)
 
 constexpr int k1f_smem_bytes(int R1) { return (256 * R1 + 16 * R1 + 256 + 240) * (int)sizeof(cd); }
-// radix-16 butterflies per thread (NB) and resident CTAs per SM the kernel is compiled for:
-// CTAs of 64..192 threads, <= 320 threads per SM so that every thread may hold ~200 registers,
-// and at least two CTAs per SM so that one CTA's barriers and load latency overlap the other's math.
-constexpr int k1f_nb(int R1) { return R1 >= 12 ? 2 : 1; }
-constexpr int k1f_threads(int R1, int NB) { return 16 * R1 / NB; }
-constexpr int k1f_min_blocks(int R1, int NB) { return 320 / k1f_threads(R1, NB) < 1 ? 1 : 320 / k1f_threads(R1, NB); }
+// Threads per CTA (NT) and resident CTAs per SM the kernel is compiled for.  A pass has NV = 16 R1
+// radix-16 butterflies; a thread owns the butterflies vt = tid, tid + NT, ... (whole warps, so the
+// lane exchange of P3 stays inside a warp).  Default: one butterfly per thread (NT = NV).
+// Measured on B200 at R1 = 20, 100k x 10k (profiles/r01_k1f_cta_shapes.txt): one CTA of 320 threads
+// per SM 25.5 ms; two CTAs of 160 threads 26.6 ms; two CTAs of 192 threads (which balances the
+// butterfly rounds 5/5/5/5 over the four SM sub-partitions instead of 3/3/2/2) 26.7 ms, because
+// the second set of pair accumulators spills (300 B / thread to local memory = L2 traffic).
+// <= 390 threads per SM keeps 168 registers per thread.
+constexpr int k1f_threads(int R1) { return 16 * R1; }
+constexpr int k1f_min_blocks(int NT) { return 390 / NT < 1 ? 1 : 390 / NT; }
 
 // ---------------------------------------------------------------------------
 // P1 twiddles: tw[k] = om^(2k + r), k < R1, from om = w_{2H}^j, two-level.
@@ -86,13 +91,13 @@ TA_HD void k1f_p1_twiddles(cd om, int r, cd* e, cd* g) {
 // device these are __syncthreads / __shfl_xor_sync, in tests/emu they are
 // cooperative-fiber versions so the very same code runs on the CPU.
 // ---------------------------------------------------------------------------
-template <int R1, int NB, class Ctx, bool PROF = false>
+template <int R1, int NT, class Ctx, bool PROF = false>
 TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid, int nblk) {
     constexpr int H = 256 * R1;
     constexpr int NV = 16 * R1;          // radix-16 butterflies per pass ("virtual threads")
-    constexpr int NT = NV / NB;          // threads per CTA; each owns NB butterflies of P2 / P3
+    constexpr int NB = (NV + NT - 1) / NT;   // butterfly rounds of P2 / P3; a thread owns vt = tid + it NT < NV
     constexpr int NG = (R1 + 3) / 4;
-    static_assert(NV % NB == 0 && NT % 32 == 0, "the lane exchange needs whole warps");
+    static_assert(NT % 32 == 0 && NV % 32 == 0, "the lane exchange needs whole warps");
     cd* buf = reinterpret_cast<cd*>(smem_raw);       // H + H/16 elements, padded layout
     cd* s_om = buf + (H + H / 16);                   // 256
     cd* s_tw2 = s_om + 256;                          // 240
@@ -113,6 +118,7 @@ TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid,
     // `dep` makes the clock read wait for a value (e.g. the last load of a batch)
 #define K1F_TICK(ph, dep) do { if (PROF && prof) { const long long tn_ = Ctx::clock_after(dep); prof[r * 16 + (ph)] += tn_ - tprev; tprev = tn_; } } while (0)
 
+    if (A.stagger > 0 && 2 * bid >= nblk) Ctx::spin(A.stagger);
     for (int atom = bid; atom < A.natoms; atom += nblk) {
         const double* ser = A.series + (size_t)atom * A.D * A.Tld;
         cd* row = reinterpret_cast<cd*>(A.by_particle + (size_t)atom * A.Tld);
@@ -164,6 +170,7 @@ TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid,
 #pragma unroll
                 for (int it = 0; it < NB; ++it) {
                     const int vt = tid + it * NT;
+                    if (NV % NT != 0 && vt >= NV) break;
                     const int p2base = (vt >> 4) * 272 + j2;     // padded address of (blk*256 + j), + 17 q
                     cd x[16];
 #pragma unroll
@@ -182,6 +189,7 @@ TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid,
                 static_for<0, NB>([&](auto iit) {
                     constexpr int it = decltype(iit)::value;
                     const int vt = tid + it * NT;
+                    if (NV % NT != 0 && vt >= NV) return;
                     const uint32_t mp = A.map[r * NV + vt];
                     const cd wb = A.wbase[r * NV + vt];
                     const int p3base = (int)(mp & 0xffffu) * 17;
@@ -216,6 +224,7 @@ TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid,
             static_for<0, NB>([&](auto iit) {
                 constexpr int it = decltype(iit)::value;
                 const int vt = tid + it * NT;
+                if (NV % NT != 0 && vt >= NV) return;
                 const uint32_t mp = A.map[r * NV + vt];
                 const cd wb = A.wbase[r * NV + vt];
                 const int p3base = (int)(mp & 0xffffu) * 17;
@@ -248,6 +257,7 @@ TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid,
 #pragma unroll
             for (int it = 0; it < NB; ++it) {
                 const int vt = tid + it * NT;
+                if (NV % NT != 0 && vt >= NV) break;
                 const int p2base = (vt >> 4) * 272 + j2;
                 cd x[16];
                 x[0] = buf[p2base];

@@ -163,6 +163,13 @@ struct DevCtx {
         return 0;
 #endif
     }
+    static TA_HD void spin(int clocks) {
+#if defined(__CUDA_ARCH__)
+        const long long t0 = clock64();
+        while (clock64() - t0 < clocks) {}
+        __syncthreads();
+#endif
+    }
     static TA_HD long long clock() {
 #if defined(__CUDA_ARCH__)
         return clock64();
@@ -182,11 +189,11 @@ struct DevCtx {
     }
 };
 
-template <int R1, int NB, bool PROF = false>
-__global__ void __launch_bounds__(k1f_threads(R1, NB), k1f_min_blocks(R1, NB))
+template <int R1, int NT, bool PROF = false>
+__global__ void __launch_bounds__(NT, k1f_min_blocks(NT))
 k1f_fft_acf(const K1FArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    k1f_body<R1, NB, DevCtx, PROF>(args, smem_raw, (int)threadIdx.x, (int)blockIdx.x, (int)gridDim.x);
+    k1f_body<R1, NT, DevCtx, PROF>(args, smem_raw, (int)threadIdx.x, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // ---------------------------------------------------------------------------

@@ -68,11 +68,17 @@ bool nccl_load(std::string* err) {
 constexpr int kNumSlabs = 3;
 constexpr int kNumDevStage = 2;
 
+// a contiguous range of this shard's particles handled by one kernel launch
+struct LaunchRange {
+    int64_t a0 = 0, n = 0;
+    cudaEvent_t ready = nullptr;   // recorded when the range's series are in place (may be null)
+};
+
 struct Shard {
     int dev = 0;
     int num_sms = 0;
     int max_smem = 0;
-    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    cudaStream_t s_compute = nullptr, s_copy = nullptr, s_k0 = nullptr;
     cudaEvent_t ev_copy_done[kNumDevStage] = {nullptr, nullptr};
     cudaEvent_t ev_k0_done[kNumDevStage] = {nullptr, nullptr};
     cudaEvent_t ev_slab[kNumSlabs] = {nullptr, nullptr, nullptr};
@@ -91,6 +97,13 @@ struct Shard {
     size_t partial_rows = 0;
     void* dstage[kNumDevStage][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     int stage_toggle = 0;
+    // whole-trajectory staging (ta_stage_bulk): particle chunks, each with all T frames
+    void* dbulk[kNumDevStage][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    size_t dbulk_bytes = 0;
+    cudaEvent_t ev_bulk_copy[kNumDevStage] = {nullptr, nullptr};
+    cudaEvent_t ev_bulk_k0[kNumDevStage] = {nullptr, nullptr};
+    std::vector<LaunchRange> chunks;    // particle ranges in staging order, with their "series ready" events
+    bool chunks_pending = false;        // the next compute call is pipelined behind the staging, chunk by chunk
     double* lagmajor_tmp = nullptr;
     size_t lagmajor_bytes = 0;
     void* l2_scratch = nullptr;
@@ -165,6 +178,7 @@ void free_problem(ta_ctx* c) {
         cudaSetDevice(s.dev);
         cudaStreamSynchronize(s.s_compute);
         cudaStreamSynchronize(s.s_copy);
+        cudaStreamSynchronize(s.s_k0);
         cudaFree(s.series); s.series = nullptr;
         cudaFree(s.by_particle); s.by_particle = nullptr;
         cudaFree(s.masses); s.masses = nullptr;
@@ -172,7 +186,14 @@ void free_problem(ta_ctx* c) {
         cudaFree(s.partial); s.partial = nullptr; s.partial_rows = 0;
         cudaFree(s.lagmajor_tmp); s.lagmajor_tmp = nullptr; s.lagmajor_bytes = 0;
         for (int b = 0; b < kNumDevStage; ++b)
-            for (int f = 0; f < 2; ++f) { cudaFree(s.dstage[b][f]); s.dstage[b][f] = nullptr; }
+            for (int f = 0; f < 2; ++f) {
+                cudaFree(s.dstage[b][f]); s.dstage[b][f] = nullptr;
+                cudaFree(s.dbulk[b][f]); s.dbulk[b][f] = nullptr;
+            }
+        s.dbulk_bytes = 0;
+        for (auto& c : s.chunks) if (c.ready) cudaEventDestroy(c.ready);
+        s.chunks.clear();
+        s.chunks_pending = false;
         cudaFree(s.tw_lo); s.tw_lo = nullptr;
         cudaFree(s.tw_hi); s.tw_hi = nullptr;
         cudaFree(s.ftab); s.ftab = nullptr;
@@ -208,9 +229,12 @@ int init_shard(ta_ctx* ctx, Shard& s, int dev) {
     CK(cudaDeviceGetAttribute(&s.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     CK(cudaStreamCreateWithFlags(&s.s_compute, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&s.s_copy, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&s.s_k0, cudaStreamNonBlocking));
     for (int b = 0; b < kNumDevStage; ++b) {
         CK(cudaEventCreateWithFlags(&s.ev_copy_done[b], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&s.ev_k0_done[b], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s.ev_bulk_copy[b], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s.ev_bulk_k0[b], cudaEventDisableTiming));
     }
     for (int i = 0; i < kNumSlabs; ++i) CK(cudaEventCreateWithFlags(&s.ev_slab[i], cudaEventDisableTiming));
     CK(cudaEventCreate(&s.ev_t0));
@@ -224,9 +248,46 @@ int sync_all(ta_ctx* ctx) {
     for (auto& s : ctx->sh) {
         CK(cudaSetDevice(s.dev));
         CK(cudaStreamSynchronize(s.s_copy));
+        CK(cudaStreamSynchronize(s.s_k0));
         CK(cudaStreamSynchronize(s.s_compute));
     }
     return TA_OK;
+}
+
+// K0 on `stream`: staged slab [nframes][n][3] (particles a0 .. a0+n-1 of the shard) -> series.
+int launch_k0(ta_ctx* ctx, Shard& s, const void* vsrc, const void* xsrc, int64_t a0, int64_t n, int64_t nframes,
+              int64_t frame0, cudaStream_t stream) {
+    dim3 block(32, 8);
+    dim3 grid((unsigned)((n + K0_AT - 1) / K0_AT), (unsigned)((nframes + K0_FR - 1) / K0_FR));
+    const int d0 = ctx->dims[0], d1 = ctx->dims[1], d2 = ctx->dims[2];
+    const bool hel = ctx->n_fields == 2;
+    double* series = s.series + (size_t)a0 * ctx->D * ctx->Tld;
+    const double* masses = s.masses ? s.masses + a0 : nullptr;
+    if (ctx->src_dtype == TA_DTYPE_F32) {
+        const float* v = (const float*)vsrc;
+        const float* x = (const float*)xsrc;
+        if (hel) k0_stage<float, true><<<grid, block, 0, stream>>>(v, x, masses, series, (int)n, (int)nframes, frame0, ctx->Tld, ctx->D, d0, d1, d2);
+        else k0_stage<float, false><<<grid, block, 0, stream>>>(v, x, masses, series, (int)n, (int)nframes, frame0, ctx->Tld, ctx->D, d0, d1, d2);
+    } else {
+        const double* v = (const double*)vsrc;
+        const double* x = (const double*)xsrc;
+        if (hel) k0_stage<double, true><<<grid, block, 0, stream>>>(v, x, masses, series, (int)n, (int)nframes, frame0, ctx->Tld, ctx->D, d0, d1, d2);
+        else k0_stage<double, false><<<grid, block, 0, stream>>>(v, x, masses, series, (int)n, (int)nframes, frame0, ctx->Tld, ctx->D, d0, d1, d2);
+    }
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return TA_OK;
+}
+
+// The particle ranges the next K1/K2/K3 call launches over: the staging chunks (each launch waits
+// for its chunk's series, so the correlation of chunk c overlaps the H2D copy of chunk c+1) right
+// after ta_stage_bulk, otherwise the whole shard in one launch.
+std::vector<LaunchRange> take_launch_ranges(Shard& s) {
+    std::vector<LaunchRange> r;
+    if (s.chunks_pending && !s.chunks.empty()) r = s.chunks;
+    else { LaunchRange all; all.a0 = 0; all.n = s.natoms; r.push_back(all); }
+    s.chunks_pending = false;
+    return r;
 }
 
 // Enqueue H2D of `nframes` frames for every shard + the K0 transposition.
@@ -250,23 +311,8 @@ int enqueue_chunk(ta_ctx* ctx, const char* const* base, size_t pitch, int64_t fr
         CK(cudaEventRecord(s.ev_copy_done[b], s.s_copy));
         if (slab_index >= 0) CK(cudaEventRecord(s.ev_slab[slab_index], s.s_copy));
         CK(cudaStreamWaitEvent(s.s_compute, s.ev_copy_done[b], 0));
-        dim3 block(32, 8);
-        dim3 grid((unsigned)((s.natoms + K0_AT - 1) / K0_AT), (unsigned)((nframes + K0_FR - 1) / K0_FR));
-        const int d0 = ctx->dims[0], d1 = ctx->dims[1], d2 = ctx->dims[2];
-        const bool hel = ctx->n_fields == 2;
-        if (ctx->src_dtype == TA_DTYPE_F32) {
-            const float* v = (const float*)s.dstage[b][0];
-            const float* x = (const float*)s.dstage[b][1];
-            if (hel) k0_stage<float, true><<<grid, block, 0, s.s_compute>>>(v, x, s.masses, s.series, (int)s.natoms, (int)nframes, frame0, ctx->Tld, ctx->D, d0, d1, d2);
-            else k0_stage<float, false><<<grid, block, 0, s.s_compute>>>(v, x, s.masses, s.series, (int)s.natoms, (int)nframes, frame0, ctx->Tld, ctx->D, d0, d1, d2);
-        } else {
-            const double* v = (const double*)s.dstage[b][0];
-            const double* x = (const double*)s.dstage[b][1];
-            if (hel) k0_stage<double, true><<<grid, block, 0, s.s_compute>>>(v, x, s.masses, s.series, (int)s.natoms, (int)nframes, frame0, ctx->Tld, ctx->D, d0, d1, d2);
-            else k0_stage<double, false><<<grid, block, 0, s.s_compute>>>(v, x, s.masses, s.series, (int)s.natoms, (int)nframes, frame0, ctx->Tld, ctx->D, d0, d1, d2);
-        }
-        CK(cudaGetLastError());
-        ctx->launches++;
+        int rc = launch_k0(ctx, s, s.dstage[b][0], s.dstage[b][1], 0, s.natoms, nframes, frame0, s.s_compute);
+        if (rc) return rc;
         CK(cudaEventRecord(s.ev_k0_done[b], s.s_compute));
     }
     ctx->frames_staged += nframes;
@@ -444,14 +490,20 @@ int launch_fft(ta_ctx* ctx, std::vector<int>* grids) {
         a.t.tw_hi = (const cplx<R>*)s.tw_hi;
         a.t.ftab = s.ftab; a.t.pair0 = s.pair0; a.t.own0 = s.own0; a.t.npairs0 = ctx->npairs0;
         a.nlo = nlo; a.nhi = nhi;
-        a.series = s.series; a.by_particle = s.by_particle; a.partial = s.partial;
-        a.natoms = (int)s.natoms; a.D = ctx->D; a.Tld = ctx->Tld;
+        a.partial = s.partial;
+        a.D = ctx->D; a.Tld = ctx->Tld;
         CK(cudaEventRecord(s.ev_ka, s.s_compute));
-        k1_fft_acf<R><<<grid, nthr, smem, s.s_compute>>>(a);
-        CK(cudaGetLastError());
+        for (const LaunchRange& rg : take_launch_ranges(s)) {
+            if (rg.ready) CK(cudaStreamWaitEvent(s.s_compute, rg.ready, 0));
+            a.series = s.series + (size_t)rg.a0 * ctx->D * ctx->Tld;
+            a.by_particle = s.by_particle + (size_t)rg.a0 * ctx->Tld;
+            a.natoms = (int)rg.n;
+            k1_fft_acf<R><<<(int)std::min<int64_t>(grid, rg.n), nthr, smem, s.s_compute>>>(a);
+            CK(cudaGetLastError());
+            ctx->launches++;
+        }
         CK(cudaEventRecord(s.ev_kb, s.s_compute));
         s.kernel_timed = true;
-        ctx->launches++;
         ctx->k1_threads = nthr; ctx->k1_smem = (int)smem; ctx->k1_grid = grid;
     }
     return TA_OK;
@@ -462,29 +514,30 @@ int env_int(const char* name, int dflt) {
     return (v && v[0]) ? atoi(v) : dflt;
 }
 
-template <int R1, int NB, bool PROF = false>
+template <int R1, int NT, bool PROF = false>
 int launch_fft_fast_r1(ta_ctx* ctx, std::vector<int>* grids) {
     const int smem = k1f_smem_bytes(R1);
-    const int nthr = k1f_threads(R1, NB);
+    const int nthr = NT;
     grids->assign(ctx->sh.size(), 0);
     for (size_t i = 0; i < ctx->sh.size(); ++i) {
         Shard& s = ctx->sh[i];
         if (s.natoms == 0) continue;
         CK(cudaSetDevice(s.dev));
-        CK(cudaFuncSetAttribute(k1f_fft_acf<R1, NB, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(k1f_fft_acf<R1, NT, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1f_fft_acf<R1, NB, PROF>, nthr, (size_t)smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1f_fft_acf<R1, NT, PROF>, nthr, (size_t)smem));
         if (occ < 1) return fail(ctx, TA_ERR_UNSUPPORTED, "fast FFT kernel does not fit on an SM");
         int grid = (int)std::min<int64_t>(s.natoms, (int64_t)s.num_sms * occ);
         (*grids)[i] = grid;
         int rc = ensure_partial(ctx, s, (size_t)grid);
         if (rc) return rc;
         K1FArgs a;
-        a.series = s.series; a.by_particle = s.by_particle; a.partial = s.partial;
+        a.partial = s.partial;
         a.omega = (const cd*)s.f_omega; a.tw2 = (const cd*)s.f_tw2; a.map = s.f_map;
         a.wbase = (const cd*)s.f_wbase; a.inv = s.f_inv;
-        a.natoms = (int)s.natoms; a.D = ctx->D; a.T = (int)ctx->T; a.nh = (int)((ctx->T + 1) / 2); a.Tld = ctx->Tld;
+        a.D = ctx->D; a.T = (int)ctx->T; a.nh = (int)((ctx->T + 1) / 2); a.Tld = ctx->Tld;
         a.prefetch = env_int("TA_B200_K1F_PREFETCH", 0);
+        a.stagger = env_int("TA_B200_K1F_STAGGER", 0);
         a.prof = nullptr;
         const bool profile = PROF;   // debug instantiation: per-phase clocks of thread 0 to stderr
         if (profile) {
@@ -492,8 +545,15 @@ int launch_fft_fast_r1(ta_ctx* ctx, std::vector<int>* grids) {
             CK(cudaMemsetAsync(a.prof, 0, (size_t)grid * 32 * sizeof(long long), s.s_compute));
         }
         CK(cudaEventRecord(s.ev_ka, s.s_compute));
-        k1f_fft_acf<R1, NB, PROF><<<grid, nthr, smem, s.s_compute>>>(a);
-        CK(cudaGetLastError());
+        for (const LaunchRange& rg : take_launch_ranges(s)) {
+            if (rg.ready) CK(cudaStreamWaitEvent(s.s_compute, rg.ready, 0));
+            a.series = s.series + (size_t)rg.a0 * ctx->D * ctx->Tld;
+            a.by_particle = s.by_particle + (size_t)rg.a0 * ctx->Tld;
+            a.natoms = (int)rg.n;
+            k1f_fft_acf<R1, NT, PROF><<<(int)std::min<int64_t>(grid, rg.n), nthr, smem, s.s_compute>>>(a);
+            CK(cudaGetLastError());
+            ctx->launches++;
+        }
         CK(cudaEventRecord(s.ev_kb, s.s_compute));
         if (profile) {
             std::vector<long long> h((size_t)grid * 32);
@@ -505,14 +565,13 @@ int launch_fft_fast_r1(ta_ctx* ctx, std::vector<int>* grids) {
             const char* nm[16] = {"P1.ld", "P1.fp", "P1.st+bar", "P2.ld", "P2.fp", "P2.st+bar", "P3.ld", "P3.fp", "P3.bar",
                                   "P3i.fp", "P3i.st+bar", "P2i.ld+fp", "P2i.st+bar", "P1i.ld+fp", "out", "-"};
             const double atoms_per_cta = (double)s.natoms / grid;
-            fprintf(stderr, "[k1f profile] R1=%d NB=%d grid=%d clocks/CTA=%.0f clocks/atom=%.0f\n", R1, NB, grid, all / grid,
+            fprintf(stderr, "[k1f profile] R1=%d NT=%d grid=%d clocks/CTA=%.0f clocks/atom=%.0f\n", R1, NT, grid, all / grid,
                     all / grid / atoms_per_cta);
             for (int q = 0; q < 32; ++q)
                 if (tot[q] > 0) fprintf(stderr, "   r%d.%-11s %5.1f%%  %7.0f clk/atom\n", q / 16, nm[q % 16], 100.0 * tot[q] / all,
                                         tot[q] / grid / atoms_per_cta);
         }
         s.kernel_timed = true;
-        ctx->launches++;
         ctx->k1_threads = nthr; ctx->k1_smem = smem; ctx->k1_grid = grid;
     }
     return TA_OK;
@@ -520,16 +579,19 @@ int launch_fft_fast_r1(ta_ctx* ctx, std::vector<int>* grids) {
 
 int launch_fft_fast(ta_ctx* ctx, std::vector<int>* grids) {
     switch (ctx->fast_r1) {
-        case 4: return launch_fft_fast_r1<4, 1>(ctx, grids);
-        case 6: return launch_fft_fast_r1<6, 1>(ctx, grids);
-        case 8: return launch_fft_fast_r1<8, 1>(ctx, grids);
-        case 10: return launch_fft_fast_r1<10, 1>(ctx, grids);
-        case 12: return launch_fft_fast_r1<12, 1>(ctx, grids);
-        case 16: return launch_fft_fast_r1<16, 1>(ctx, grids);
-        case 20:
-            if (env_int("TA_B200_K1F_PROFILE", 0)) return launch_fft_fast_r1<20, 1, true>(ctx, grids);
-            return env_int("TA_B200_K1F_NB", 1) == 2 ? launch_fft_fast_r1<20, 2>(ctx, grids)
-                                                     : launch_fft_fast_r1<20, 1>(ctx, grids);
+        case 4: return launch_fft_fast_r1<4, k1f_threads(4)>(ctx, grids);
+        case 6: return launch_fft_fast_r1<6, k1f_threads(6)>(ctx, grids);
+        case 8: return launch_fft_fast_r1<8, k1f_threads(8)>(ctx, grids);
+        case 10: return launch_fft_fast_r1<10, k1f_threads(10)>(ctx, grids);
+        case 12: return launch_fft_fast_r1<12, k1f_threads(12)>(ctx, grids);
+        case 16: return launch_fft_fast_r1<16, k1f_threads(16)>(ctx, grids);
+        case 20: {
+            if (env_int("TA_B200_K1F_PROFILE", 0)) return launch_fft_fast_r1<20, k1f_threads(20), true>(ctx, grids);
+            const int nt = env_int("TA_B200_K1F_NT", k1f_threads(20));   // experiments: two CTAs per SM
+            if (nt == 192) return launch_fft_fast_r1<20, 192>(ctx, grids);
+            if (nt == 160) return launch_fft_fast_r1<20, 160>(ctx, grids);
+            return launch_fft_fast_r1<20, k1f_threads(20)>(ctx, grids);
+        }
     }
     return fail(ctx, TA_ERR_UNSUPPORTED, "no fast FFT instantiation for R1=" + std::to_string(ctx->fast_r1));
 }
@@ -560,14 +622,20 @@ int launch_windowed(ta_ctx* ctx, double denom, std::vector<int>* grids) {
         int rc = ensure_partial(ctx, s, (size_t)grid);
         if (rc) return rc;
         WinArgs a;
-        a.series = s.series; a.by_particle = s.by_particle; a.partial = s.partial;
-        a.natoms = (int)s.natoms; a.D = ctx->D; a.T = T; a.Tld = ctx->Tld; a.denom = denom;
+        a.partial = s.partial;
+        a.D = ctx->D; a.T = T; a.Tld = ctx->Tld; a.denom = denom;
         CK(cudaEventRecord(s.ev_ka, s.s_compute));
-        k_windowed<R, MODE><<<grid, nthr, smem, s.s_compute>>>(a);
-        CK(cudaGetLastError());
+        for (const LaunchRange& rg : take_launch_ranges(s)) {
+            if (rg.ready) CK(cudaStreamWaitEvent(s.s_compute, rg.ready, 0));
+            a.series = s.series + (size_t)rg.a0 * ctx->D * ctx->Tld;
+            a.by_particle = s.by_particle + (size_t)rg.a0 * ctx->Tld;
+            a.natoms = (int)rg.n;
+            k_windowed<R, MODE><<<(int)std::min<int64_t>(grid, rg.n), nthr, smem, s.s_compute>>>(a);
+            CK(cudaGetLastError());
+            ctx->launches++;
+        }
         CK(cudaEventRecord(s.ev_kb, s.s_compute));
         s.kernel_timed = true;
-        ctx->launches++;
     }
     return TA_OK;
 }
@@ -601,6 +669,8 @@ void destroy_ctx(ta_ctx* c) {
         for (int b = 0; b < kNumDevStage; ++b) {
             if (s.ev_copy_done[b]) cudaEventDestroy(s.ev_copy_done[b]);
             if (s.ev_k0_done[b]) cudaEventDestroy(s.ev_k0_done[b]);
+            if (s.ev_bulk_copy[b]) cudaEventDestroy(s.ev_bulk_copy[b]);
+            if (s.ev_bulk_k0[b]) cudaEventDestroy(s.ev_bulk_k0[b]);
         }
         for (int i = 0; i < kNumSlabs; ++i) if (s.ev_slab[i]) cudaEventDestroy(s.ev_slab[i]);
         if (s.ev_t0) cudaEventDestroy(s.ev_t0);
@@ -609,6 +679,7 @@ void destroy_ctx(ta_ctx* c) {
         if (s.ev_kb) cudaEventDestroy(s.ev_kb);
         if (s.s_compute) cudaStreamDestroy(s.s_compute);
         if (s.s_copy) cudaStreamDestroy(s.s_copy);
+        if (s.s_k0) cudaStreamDestroy(s.s_k0);
     }
     delete c;
 }
@@ -739,6 +810,7 @@ int ta_stage_begin(ta_ctx* ctx, int64_t T, int64_t N, int D, const int* dims, in
         ctx->precision = precision;
         ctx->frames_staged = 0;
         ctx->cur_slab = -1;
+        for (auto& s : ctx->sh) s.chunks_pending = false;
         for (auto& s : ctx->sh) {
             if (s.natoms == 0 || n_fields != 2) continue;
             CK(cudaSetDevice(s.dev));
@@ -847,15 +919,62 @@ int ta_stage_bulk(ta_ctx* ctx, const void* const* fields, int64_t src_atoms, int
         return fail(ctx, TA_ERR_INVALID, "bad frame / atom window");
     const size_t src_row = (size_t)src_atoms * 3 * ctx->elt;
     const size_t pitch = (size_t)frame_step * src_row;
-    for (int64_t f0 = 0; f0 < nframes; f0 += ctx->slab_frames) {
-        const int64_t nf = std::min<int64_t>(ctx->slab_frames, nframes - f0);
-        const char* base[2] = {nullptr, nullptr};
-        for (int f = 0; f < ctx->n_fields; ++f)
-            base[f] = (const char*)fields[f] + (size_t)(frame_first + f0 * frame_step) * src_row +
-                      (size_t)atom_first * 3 * ctx->elt;
-        int rc = enqueue_chunk(ctx, base, pitch, f0, nf, -1);
-        if (rc) return rc;
+    const int64_t T = ctx->T;
+    // Particle chunks, each carrying all T frames (a 2-D copy: T rows of chunk*3 values), so that the
+    // correlation kernel of a chunk can start as soon as the chunk has landed: ~256 MB per chunk and
+    // field, a multiple of 296 particles (two resident CTAs on each of the 148 SMs).
+    const int64_t want = std::max<int64_t>(1, ((int64_t)256 << 20) / (T * 3 * (int64_t)ctx->elt));
+    const int64_t env_chunk = env_int("TA_B200_BULK_CHUNK", 0);
+    for (auto& s : ctx->sh) {
+        if (s.natoms == 0) continue;
+        CK(cudaSetDevice(s.dev));
+        int64_t CA = env_chunk > 0 ? env_chunk : std::max<int64_t>(296, want / 296 * 296);
+        CA = std::min<int64_t>(CA, s.natoms);
+        const size_t need = (size_t)T * CA * 3 * ctx->elt;
+        if (s.dbulk_bytes < need) {
+            for (int b = 0; b < kNumDevStage; ++b)
+                for (int f = 0; f < ctx->n_fields; ++f) {
+                    cudaFree(s.dbulk[b][f]); s.dbulk[b][f] = nullptr;
+                }
+            s.dbulk_bytes = 0;
+            const int nbuf = (s.natoms > CA) ? kNumDevStage : 1;
+            for (int b = 0; b < nbuf; ++b)
+                for (int f = 0; f < ctx->n_fields; ++f) CK(cudaMalloc(&s.dbulk[b][f], need));
+            s.dbulk_bytes = need;
+            for (int b = 0; b < kNumDevStage; ++b) {
+                CK(cudaEventRecord(s.ev_bulk_k0[b], s.s_k0));
+                CK(cudaEventRecord(s.ev_bulk_copy[b], s.s_copy));
+            }
+        }
+        const size_t nchunks = (size_t)((s.natoms + CA - 1) / CA);
+        while (s.chunks.size() > nchunks) { cudaEventDestroy(s.chunks.back().ready); s.chunks.pop_back(); }
+        while (s.chunks.size() < nchunks) {
+            LaunchRange r;
+            CK(cudaEventCreateWithFlags(&r.ready, cudaEventDisableTiming));
+            s.chunks.push_back(r);
+        }
+        for (size_t c = 0; c < nchunks; ++c) {
+            const int b = (s.dbulk[1][0] != nullptr) ? (int)(c & 1) : 0;
+            const int64_t a0 = (int64_t)c * CA, n = std::min<int64_t>(CA, s.natoms - a0);
+            const size_t width = (size_t)n * 3 * ctx->elt;
+            CK(cudaStreamWaitEvent(s.s_copy, s.ev_bulk_k0[b], 0));     // K0 has consumed this buffer
+            for (int f = 0; f < ctx->n_fields; ++f) {
+                const char* src = (const char*)fields[f] + (size_t)frame_first * src_row +
+                                  (size_t)(atom_first + s.atom0 + a0) * 3 * ctx->elt;
+                CK(cudaMemcpy2DAsync(s.dbulk[b][f], width, src, pitch, width, (size_t)T, cudaMemcpyHostToDevice, s.s_copy));
+            }
+            CK(cudaEventRecord(s.ev_bulk_copy[b], s.s_copy));
+            CK(cudaStreamWaitEvent(s.s_k0, s.ev_bulk_copy[b], 0));
+            int rc = launch_k0(ctx, s, s.dbulk[b][0], s.dbulk[b][1], a0, n, T, 0, s.s_k0);
+            if (rc) return rc;
+            CK(cudaEventRecord(s.ev_bulk_k0[b], s.s_k0));
+            s.chunks[c].a0 = a0;
+            s.chunks[c].n = n;
+            CK(cudaEventRecord(s.chunks[c].ready, s.s_k0));
+        }
+        s.chunks_pending = true;
     }
+    ctx->frames_staged = T;
     return TA_OK;
 }
 
