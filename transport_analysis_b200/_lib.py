@@ -63,7 +63,7 @@ def load_library(path: str | None = None) -> ctypes.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or LIB_PATH
+    path = path or os.environ.get("TA_B200_LIB") or LIB_PATH   # TA_B200_LIB: an experimental build of the same ABI
     if not os.path.exists(path):
         raise BackendError(
             f"{path} not found: the CUDA backend has not been built "
