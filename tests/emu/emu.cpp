@@ -59,31 +59,21 @@ static int run_fft(const double* series, int T, int D, int Tld, int nthr, double
 
 template <typename R>
 static int run_win(const double* series, int T, int D, int Tld, int mode, int nwarps, double* res) {
-    int ne = win_smem_elems(T);
-    std::vector<R> S(ne);
-    int nlb = win_num_lag_blocks(T), npairs = win_num_pairs(nlb);
-    for (int k = 0; k < T; ++k) res[k] = 0.0;
-    for (int d = 0; d < D; ++d) {
-        std::fill(S.begin(), S.end(), (R)0);
-        for (int x = 0; x < T; ++x) S[win_addr(x)] = (R)series[(size_t)d * Tld + x];
-        for (int w = 0; w < nwarps; ++w) {
-            for (int pair = w; pair < npairs; pair += nwarps) {
-                int kbs[2];
-                win_pair_blocks(pair, nlb, &kbs[0], &kbs[1]);
-                for (int h = 0; h < 2; ++h) {
-                    int kb = kbs[h];
-                    if (kb < 0) continue;
-                    R tot[16] = {0};
-                    for (int lane = 0; lane < 32; ++lane) {
-                        R acc[16] = {0};
-                        if (mode == TA_WIN_PRODUCT) win_lane_accumulate<R, TA_WIN_PRODUCT>(lane, 32, S.data(), T, kb, acc);
-                        else win_lane_accumulate<R, TA_WIN_SQDIFF>(lane, 32, S.data(), T, kb, acc);
-                        for (int m = 0; m < 16; ++m) tot[m] += acc[m];
-                    }
-                    for (int m = 0; m < 16; ++m) if (kb * 16 + m < T) res[kb * 16 + m] += (double)tot[m];
-                }
-            }
-        }
+    // the kernel body itself (windowed_core.cuh win_body) for one particle, one CTA of nwarps warps;
+    // returns the un-normalised lag sums (row * (T - k) [* D * denom])
+    const int ne = win_smem_elems(T);
+    std::vector<unsigned char> smem((size_t)((ne + 1) & ~1) * sizeof(R) + (size_t)T * sizeof(double) + 64);
+    unsigned char* sm = smem.data() + (16 - ((uintptr_t)smem.data() & 15)) % 16;
+    std::vector<double> row(Tld, 0.0), partial(Tld, 0.0);
+    WinArgs a;
+    a.series = series; a.by_particle = row.data(); a.partial = partial.data();
+    a.natoms = 1; a.D = D; a.T = T; a.Tld = Tld; a.denom = 1.0;
+    const int nthr = 32 * nwarps;
+    if (mode == TA_WIN_PRODUCT) emu::run_cta(nthr, [&](int tid) { win_body<R, TA_WIN_PRODUCT, emu::EmuCtx>(a, sm, tid, nthr, 0, 1); });
+    else emu::run_cta(nthr, [&](int tid) { win_body<R, TA_WIN_SQDIFF, emu::EmuCtx>(a, sm, tid, nthr, 0, 1); });
+    for (int k = 0; k < T; ++k) {
+        if (row[k] != partial[k]) return -2;
+        res[k] = row[k] * (double)(T - k) * (mode == TA_WIN_PRODUCT ? 1.0 : (double)D);
     }
     return 0;
 }

@@ -115,7 +115,8 @@ inline double shfl_xor(double v, int mask) {
 
 struct EmuCtx {
     static void sync() { sync_block(); }
-    static double shfl_xor16(double v) { return shfl_xor(v, 16); }
+    static double shfl_xor16(double v) { return emu::shfl_xor(v, 16); }
+    static double shfl_xor(double v, int mask) { return emu::shfl_xor(v, mask); }
     static void prefetch_l2(const void*, size_t, int, int) {}
     static long long clock() { return 0; }
     static void spin(int) {}

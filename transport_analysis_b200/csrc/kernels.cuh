@@ -133,6 +133,13 @@ struct DevCtx {
         __syncthreads();
 #endif
     }
+    static TA_HD double shfl_xor(double v, int mask) {
+#if defined(__CUDA_ARCH__)
+        return __shfl_xor_sync(0xffffffffu, v, mask);
+#else
+        return v;
+#endif
+    }
     static TA_HD double shfl_xor16(double v) {
 #if defined(__CUDA_ARCH__)
         return __shfl_xor_sync(0xffffffffu, v, 16);
@@ -201,74 +208,13 @@ k1f_fft_acf(const K1FArgs args) {
 //   MODE = TA_WIN_PRODUCT: vacf[k]  = sum_d sum_i g_d[i] g_d[i+k] / (T-k)
 //   MODE = TA_WIN_SQDIFF : visc[k]  = sum_d sum_i (g_d[i]-g_d[i+k])^2 / (D (T-k)) / denom
 // ---------------------------------------------------------------------------
-struct WinArgs {
-    const double* series;   // [natoms][D][Tld]
-    double* by_particle;    // [natoms][Tld]
-    double* partial;        // [gridDim.x][Tld]
-    int natoms, D, T;
-    long long Tld;
-    double denom;           // Helfand: 2 kB <V> temp_avg ; VACF: unused
-};
-
 constexpr int KW_MAX_THREADS = 512;
 
 template <typename R, int MODE>
 __global__ void __launch_bounds__(KW_MAX_THREADS)
 k_windowed(const WinArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int T = args.T;
-    const int ne = win_smem_elems(T);
-    R* S = reinterpret_cast<R*>(smem_raw);
-    double* res = reinterpret_cast<double*>(S + ((ne + 1) & ~1));
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
-    const int nlb = win_num_lag_blocks(T), npairs = win_num_pairs(nlb);
-    double* partial = args.partial + (size_t)blockIdx.x * args.Tld;
-
-    for (int a = blockIdx.x; a < args.natoms; a += gridDim.x) {
-        for (int k = tid; k < T; k += nthr) res[k] = 0.0;
-        for (int d = 0; d < args.D; ++d) {
-            const double* ser = args.series + ((size_t)a * args.D + d) * args.Tld;
-            __syncthreads();   // previous series fully consumed
-            for (int x = tid; x < ne; x += nthr) S[x] = (R)0;
-            __syncthreads();
-            for (int x = tid; x < T; x += nthr) S[win_addr(x)] = (R)ser[x];
-            __syncthreads();
-            for (int pair = warp; pair < npairs; pair += nwarps) {
-                int kbs[2];
-                win_pair_blocks(pair, nlb, &kbs[0], &kbs[1]);
-#pragma unroll 1
-                for (int h = 0; h < 2; ++h) {
-                    const int kb = kbs[h];
-                    if (kb < 0) continue;
-                    R acc[TA_WIN_LAGS];
-#pragma unroll
-                    for (int m = 0; m < TA_WIN_LAGS; ++m) acc[m] = (R)0;
-                    win_lane_accumulate<R, MODE>(lane, 32, S, T, kb, acc);
-                    double mine = 0.0;
-#pragma unroll
-                    for (int m = 0; m < TA_WIN_LAGS; ++m) {
-                        double v = (double)acc[m];
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                        if (lane == m) mine = v;
-                    }
-                    const int k = kb * TA_WIN_LAGS + lane;
-                    if (lane < TA_WIN_LAGS && k < T) res[k] += mine;   // lag k is owned by this warp only
-                }
-            }
-        }
-        __syncthreads();
-        double* row = args.by_particle + (size_t)a * args.Tld;
-        for (int k = tid; k < T; k += nthr) {
-            double val;
-            if (MODE == TA_WIN_PRODUCT) val = res[k] / (double)(T - k);
-            else val = res[k] / ((double)args.D * (double)(T - k)) / args.denom;
-            row[k] = val;
-            partial[k] += val;
-        }
-        __syncthreads();
-    }
+    win_body<R, MODE, DevCtx>(args, smem_raw, (int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // ---------------------------------------------------------------------------

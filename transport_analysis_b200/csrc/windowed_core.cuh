@@ -10,8 +10,9 @@
 // Work decomposition: lags are grouped in blocks of 16 (k0 = 16 kb); the
 // origins i of a block are cut into chunks of 16; one lane owns one 16 x 16
 // (origin x lag) tile at a time: 16 + 31 series values from shared memory feed
-// 256 FMAs.  The 32 lanes of a warp take chunks c = lane, lane + 32, ... of
-// the same lag block and their 16 partial sums are tree-reduced with shuffles.
+// 256 FMAs.  A warp works on a PAIR of lag blocks (kb, nlb-1-kb); its lanes are
+// split between the two blocks in proportion to their chunk counts and the
+// 16 partial sums of each block are reduced with halving shuffle exchanges.
 //
 // Shared-memory layout of one series: element x lives at x + 2 * (x >> 4)
 // (two pad doubles per 16), so the 128-bit loads of the 32 lanes -- whose
@@ -58,31 +59,170 @@ TA_HD void win_tile(const R* S, int i0, int k0, int T, R* acc) {
     }
 }
 
-// Partial sums of one lane for lag block kb: acc[m] += sum over the lane's
-// tiles of f(g[i], g[i + 16 kb + m]).
-template <typename R, int MODE>
-TA_HD void win_lane_accumulate(int lane, int nlanes, const R* S, int T, int kb, R* acc) {
-    const int k0 = kb * TA_WIN_LAGS;
-    const int ni = T - k0;                       // valid origins for lag k0
-    const int nch = (ni + TA_WIN_CHUNK - 1) / TA_WIN_CHUNK;
-    for (int c = lane; c < nch; c += nlanes) {
-        const int i0 = c * TA_WIN_CHUNK;
-        if (MODE == TA_WIN_PRODUCT) {
-            win_tile<R, MODE, false>(S, i0, k0, T, acc);   // zero tail makes masking unnecessary
-        } else {
-            if (i0 + 15 + k0 + 15 >= T) win_tile<R, MODE, true>(S, i0, k0, T, acc);
-            else win_tile<R, MODE, false>(S, i0, k0, T, acc);
-        }
-    }
+// Chunks of lag block kb whose 16 x 16 tile needs no validity mask.  PRODUCT: all of them (the zero
+// tail makes out-of-range products vanish).  SQDIFF: those with i0 + 15 + k0 + 15 < T; the remaining
+// one to three "tail" chunks per block are handled by win_tail_block.
+template <int MODE>
+TA_HD int win_num_chunks(int T, int kb) { return (T - kb * TA_WIN_LAGS + TA_WIN_CHUNK - 1) / TA_WIN_CHUNK; }
+template <int MODE>
+TA_HD int win_full_chunks(int T, int kb) {
+    if (MODE == TA_WIN_PRODUCT) return win_num_chunks<MODE>(T, kb);
+    const int n = T - kb * TA_WIN_LAGS - 30;
+    return n > 0 ? (n + TA_WIN_CHUNK - 1) / TA_WIN_CHUNK : 0;
 }
 
-// Lag-block schedule of one warp: blocks are paired (kb, nlb-1-kb) so that
-// every pair carries about T + 16 origins; warp w takes pairs w, w + nwarps...
+// Lag-block schedule of one warp: blocks are paired (kb, nlb-1-kb) so that every pair carries about
+// T + 16 origins; warp w takes pairs w, w + nwarps, ...  The 32 lanes are split between the two
+// blocks of a pair in proportion to their chunk counts (lanes [0, La) -> first block), so that a
+// pair costs ceil-ish((nfa + nfb) / 32) tile rounds instead of ceil(nfa / 32) + ceil(nfb / 32).
 TA_HD int win_num_pairs(int nlb) { return (nlb + 1) / 2; }
 TA_HD void win_pair_blocks(int pair, int nlb, int* kb_a, int* kb_b) {
     *kb_a = pair;
     int other = nlb - 1 - pair;
     *kb_b = (other != pair) ? other : -1;
+}
+TA_HD int win_rounds(int nfa, int nfb, int La) {
+    const int ra = nfa > 0 ? (nfa + La - 1) / La : 0;
+    const int rb = nfb > 0 ? (nfb + (32 - La) - 1) / (32 - La) : 0;
+    return ra > rb ? ra : rb;
+}
+TA_HD int win_split(int nfa, int nfb) {
+    if (nfb <= 0) return 32;
+    if (nfa <= 0) return 0;
+    int La = (32 * nfa + (nfa + nfb) / 2) / (nfa + nfb);
+    La = La < 1 ? 1 : (La > 31 ? 31 : La);
+    int best = La, br = win_rounds(nfa, nfb, La);
+    for (int c = La - 1; c <= La + 1; c += 2)
+        if (c >= 1 && c <= 31 && win_rounds(nfa, nfb, c) < br) { best = c; br = win_rounds(nfa, nfb, c); }
+    return best;
+}
+
+// Sum over the lanes with `take` set of their 16 partial sums, by halving exchanges (16 shuffles of
+// a double instead of 16 x 5): on return lane l holds the total of lag  m = l >> 1.
+template <class Ctx, typename R>
+TA_HD double win_reduce16(const R* acc, bool take, int lane) {
+    double v[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) v[m] = take ? (double)acc[m] : 0.0;
+    {
+        const bool hi = (lane & 16) != 0;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const double send = hi ? v[m] : v[m + 8], keep = hi ? v[m + 8] : v[m];
+            v[m] = keep + Ctx::shfl_xor(send, 16);
+        }
+    }
+    {
+        const bool hi = (lane & 8) != 0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const double send = hi ? v[m] : v[m + 4], keep = hi ? v[m + 4] : v[m];
+            v[m] = keep + Ctx::shfl_xor(send, 8);
+        }
+    }
+    {
+        const bool hi = (lane & 4) != 0;
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            const double send = hi ? v[m] : v[m + 2], keep = hi ? v[m + 2] : v[m];
+            v[m] = keep + Ctx::shfl_xor(send, 4);
+        }
+    }
+    {
+        const bool hi = (lane & 2) != 0;
+        const double send = hi ? v[0] : v[1], keep = hi ? v[1] : v[0];
+        v[0] = keep + Ctx::shfl_xor(send, 2);
+    }
+    return v[0] + Ctx::shfl_xor(v[0], 1);
+}
+
+struct WinArgs {
+    const double* series;   // [natoms][D][Tld]
+    double* by_particle;    // [natoms][Tld]
+    double* partial;        // [nblk][Tld]
+    int natoms, D, T;
+    long long Tld;
+    double denom;           // Helfand: 2 kB <V> temp_avg ; VACF: unused
+};
+
+// ---------------------------------------------------------------------------
+// The kernel body for one CTA (persistent over particles bid, bid + nblk, ...).  Ctx supplies
+// sync() and shfl_xor(); tests/emu runs the same code on the CPU under cooperative fibers.
+//   MODE = TA_WIN_PRODUCT: vacf[k] = sum_d sum_i g_d[i] g_d[i+k] / (T-k)
+//   MODE = TA_WIN_SQDIFF : visc[k] = sum_d sum_i (g_d[i]-g_d[i+k])^2 / (D (T-k)) / denom
+// ---------------------------------------------------------------------------
+template <typename R, int MODE, class Ctx>
+TA_HD void win_body(const WinArgs& A, unsigned char* smem_raw, int tid, int nthr, int bid, int nblk) {
+    const int T = A.T;
+    const int ne = win_smem_elems(T);
+    R* S = reinterpret_cast<R*>(smem_raw);
+    double* res = reinterpret_cast<double*>(S + ((ne + 1) & ~1));
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    const int nlb = win_num_lag_blocks(T), npairs = win_num_pairs(nlb);
+    double* partial = A.partial + (size_t)bid * A.Tld;
+
+    for (int a = bid; a < A.natoms; a += nblk) {
+        for (int k = tid; k < T; k += nthr) res[k] = 0.0;
+        for (int d = 0; d < A.D; ++d) {
+            const double* ser = A.series + ((size_t)a * A.D + d) * A.Tld;
+            Ctx::sync();   // previous series fully consumed
+            for (int x = tid; x < ne; x += nthr) S[x] = (R)0;
+            Ctx::sync();
+            for (int x = tid; x < T; x += nthr) S[win_addr(x)] = (R)ser[x];
+            Ctx::sync();
+            // ---- unmasked tiles: a warp per block pair, lanes split between the two blocks
+            for (int pair = warp; pair < npairs; pair += nwarps) {
+                int ka, kb;
+                win_pair_blocks(pair, nlb, &ka, &kb);
+                const int nfa = win_full_chunks<MODE>(T, ka);
+                const int nfb = kb >= 0 ? win_full_chunks<MODE>(T, kb) : 0;
+                if (nfa + nfb == 0) continue;
+                const int La = win_split(nfa, nfb);
+                const bool mine_a = lane < La;
+                const int k0 = (mine_a ? ka : kb) * TA_WIN_LAGS;
+                const int cnt = mine_a ? nfa : nfb;
+                const int stride = mine_a ? La : 32 - La;
+                R acc[TA_WIN_LAGS];
+#pragma unroll
+                for (int m = 0; m < TA_WIN_LAGS; ++m) acc[m] = (R)0;
+                for (int c = mine_a ? lane : lane - La; c < cnt; c += stride)
+                    win_tile<R, MODE, false>(S, c * TA_WIN_CHUNK, k0, T, acc);
+                const double ra = win_reduce16<Ctx, R>(acc, mine_a, lane);
+                const double rb = (nfb > 0) ? win_reduce16<Ctx, R>(acc, !mine_a, lane) : 0.0;
+                if ((lane & 1) == 0) {      // this warp is the only one that touches the pair's lags in this phase
+                    const int m = lane >> 1;
+                    if (nfa > 0 && ka * TA_WIN_LAGS + m < T) res[ka * TA_WIN_LAGS + m] += ra;
+                    if (nfb > 0 && kb * TA_WIN_LAGS + m < T) res[kb * TA_WIN_LAGS + m] += rb;
+                }
+            }
+            if (MODE == TA_WIN_SQDIFF) {
+                // ---- masked tail tiles: one lane per lag block (no cross-lane reduction, fixed order)
+                Ctx::sync();
+                for (int blk = tid; blk < nlb; blk += nthr) {
+                    const int k0 = blk * TA_WIN_LAGS;
+                    R acc[TA_WIN_LAGS];
+#pragma unroll
+                    for (int m = 0; m < TA_WIN_LAGS; ++m) acc[m] = (R)0;
+                    const int nch = win_num_chunks<MODE>(T, blk);
+                    for (int c = win_full_chunks<MODE>(T, blk); c < nch; ++c)
+                        win_tile<R, MODE, true>(S, c * TA_WIN_CHUNK, k0, T, acc);
+#pragma unroll
+                    for (int m = 0; m < TA_WIN_LAGS; ++m)
+                        if (k0 + m < T) res[k0 + m] += (double)acc[m];
+                }
+            }
+        }
+        Ctx::sync();
+        double* row = A.by_particle + (size_t)a * A.Tld;
+        for (int k = tid; k < T; k += nthr) {
+            double val;
+            if (MODE == TA_WIN_PRODUCT) val = res[k] / (double)(T - k);
+            else val = res[k] / ((double)A.D * (double)(T - k)) / A.denom;
+            row[k] = val;
+            partial[k] += val;
+        }
+        Ctx::sync();
+    }
 }
 
 }  // namespace ta
