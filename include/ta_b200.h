@@ -17,6 +17,8 @@
  *                             + tidynamics.acf (un-vendored dependency, call site :211-213)
  *   ta_vacf_windowed          VelocityAutocorr._conclude_simple transport_analysis/velocityautocorr.py:217-238
  *   ta_helfand                ViscosityHelfand._conclude     transport_analysis/viscosity.py:201-233
+ *   ta_helfand_fft            the same result by an FFT route (opt-in; not in the shipped reference,
+ *                             flagged as future work in docs/tutorials/helfand_dev_toy_system.ipynb:134)
  *   ta_fetch_by_particle      results.vacf_by_particle / results.visc_by_particle
  *                             (velocityautocorr.py:145-147, viscosity.py:117-119, :229-231)
  *
@@ -106,6 +108,12 @@ int ta_vacf_fft(ta_ctx* ctx, double* ts_out);
 int ta_vacf_windowed(ta_ctx* ctx, double* ts_out);
 int ta_helfand(ta_ctx* ctx, const double* volumes /*[T]*/, double boltzmann, double temp_avg,
                double* ts_out);
+/* Opt-in O(T log T) route to the same Helfand MSD: sum (g[i]-g[i+k])^2 = S1[k] - 2 S2[k] with S2 from
+ * the FFT autocorrelation kernel (idea noted in docs/tutorials/helfand_dev_toy_system.ipynb:134).
+ * The difference cancels: relative error ~ 1e-16 * S1/MSD, largest at small lags (about 1e-8 for
+ * T = 5,000 random-walk moments), so it is NOT the default and not held to the 1e-10 bar. */
+int ta_helfand_fft(ta_ctx* ctx, const double* volumes /*[T]*/, double boltzmann, double temp_avg,
+                   double* ts_out);
 int ta_fetch_by_particle(ta_ctx* ctx, int64_t atom0, int64_t natoms, int layout, double* out);
 
 /* Device-side timing of whatever is enqueued between begin and end (CUDA

@@ -121,3 +121,24 @@ def test_standin_frame_slicing_matches_range():
         assert p.n_frames == len(expect)
         assert list(p.frames) == expect
         np.testing.assert_array_equal(p.times, np.array(expect, dtype=float))
+
+
+def test_running_viscosity_reproduces_the_demo_notebook(u):
+    """docs/tutorials/viscosity_early_demo.ipynb: timeseries (:47-48) and the running viscosity it
+    prints (:133-134) for a 10-frame run whose frame times are 1..10."""
+    ts = np.array([0.0, 96.43610866, 94.54194053, 86.22211806, 85.18650814, 93.90772559, 108.7836928, 97.7115102,
+                   96.4890803, 139.72614008])
+    want = np.array([48.21805433, 31.51398018, 21.55552951, 17.03730163, 15.6512876, 15.54052754, 12.21393878,
+                     10.72100892, 13.97261401])
+    h = VH(u.atoms)
+    with pytest.raises(RuntimeError, match="must be run"):
+        h.running_viscosity
+    h.results.timeseries = ts
+    h.times = np.arange(1.0, 11.0)
+    h.n_frames = 10
+    np.testing.assert_allclose(h.running_viscosity, want, rtol=1e-8)
+
+
+def test_helfand_fft_route_needs_fp64(u):
+    with pytest.raises(ValueError, match="fp64"):
+        VH(u.atoms, fft=True, precision="fp32")

@@ -39,6 +39,7 @@ _SIGNATURES = {
     "ta_vacf_fft": (c_int, [c_void_p, POINTER(c_double)]),
     "ta_vacf_windowed": (c_int, [c_void_p, POINTER(c_double)]),
     "ta_helfand": (c_int, [c_void_p, POINTER(c_double), c_double, c_double, POINTER(c_double)]),
+    "ta_helfand_fft": (c_int, [c_void_p, POINTER(c_double), c_double, c_double, POINTER(c_double)]),
     "ta_fetch_by_particle": (c_int, [c_void_p, c_int64, c_int64, c_int, POINTER(c_double)]),
     "ta_timer_begin": (c_int, [c_void_p]),
     "ta_timer_end": (c_int, [c_void_p, POINTER(c_float)]),
@@ -205,13 +206,15 @@ class Context:
         self._check(self._lib.ta_vacf_windowed(self._h, _dptr(ts)), "ta_vacf_windowed")
         return ts
 
-    def helfand(self, volumes, boltzmann: float, temp_avg: float) -> np.ndarray:
+    def helfand(self, volumes, boltzmann: float, temp_avg: float, fft: bool = False) -> np.ndarray:
+        """``fft=False``: the direct windowed MSD (kernel K3, reference parity).  ``fft=True``: the
+        opt-in O(T log T) route S1 - 2 S2 (kernels K1 + K5; cancellation-limited accuracy)."""
         vol = np.ascontiguousarray(volumes, dtype=np.float64)
         if vol.shape != (self.T,):
             raise ValueError("volumes must have one entry per analysed frame")
         ts = np.empty(self.T, dtype=np.float64)
-        self._check(self._lib.ta_helfand(self._h, _dptr(vol), float(boltzmann), float(temp_avg), _dptr(ts)),
-                    "ta_helfand")
+        fn, name = (self._lib.ta_helfand_fft, "ta_helfand_fft") if fft else (self._lib.ta_helfand, "ta_helfand")
+        self._check(fn(self._h, _dptr(vol), float(boltzmann), float(temp_avg), _dptr(ts)), name)
         return ts
 
     def fetch_by_particle(self, atom0=0, natoms=None, lag_major_copy=False) -> np.ndarray:

@@ -218,6 +218,75 @@ k_windowed(const WinArgs args) {
 }
 
 // ---------------------------------------------------------------------------
+// K5: finishing pass of the opt-in FFT route for the Helfand MSD
+// (docs/tutorials/helfand_dev_toy_system.ipynb:134 "consider whether fft is possible later";
+// same quantity as ViscosityHelfand._conclude, viscosity.py:201-233):
+//   sum_i (g[i] - g[i+k])^2 = S1[k] - 2 S2[k],
+//   S2[k] = sum_i g[i] g[i+k]                      (K1 left  sum_d S2_d[k] / (T-k)  in by_particle)
+//   S1[k] = sum_{i<T-k} g[i]^2 + sum_{i>=k} g[i]^2 (from one prefix sum of q[i] = sum_d g_d[i]^2)
+// One CTA per particle at a time; prefix sums in shared memory.  The difference cancels, so the
+// relative error grows like eps * S1 / MSD (largest at small lags): this route is opt-in.
+// ---------------------------------------------------------------------------
+struct HelfandFftArgs {
+    const double* series;   // [natoms][D][Tld]
+    double* by_particle;    // [natoms][Tld]  in: sum_d acf_d ; out: viscosity function
+    double* partial;        // [gridDim.x][Tld]
+    int natoms, D, T;
+    long long Tld;
+    double denom;           // 2 kB <V> temp_avg
+};
+
+constexpr int K5_THREADS = 256;
+
+__global__ void __launch_bounds__(K5_THREADS)
+k5_helfand_fft_finish(const HelfandFftArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* P = reinterpret_cast<double*>(smem_raw);   // P[j] = sum_{i<j} q[i], j = 0..T
+    __shared__ double wsum[K5_THREADS / 32];
+    const int T = a.T, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int seg = (T + K5_THREADS - 1) / K5_THREADS;
+    const int lo = min(T, tid * seg), hi = min(T, lo + seg);
+    double* partial = a.partial + (size_t)blockIdx.x * a.Tld;
+    for (int n = blockIdx.x; n < a.natoms; n += gridDim.x) {
+        const double* ser = a.series + (size_t)n * a.D * a.Tld;
+        __syncthreads();   // previous particle's P fully consumed
+        // q[i] into P[i + 1] (coalesced), then a three-level inclusive scan
+        for (int i = tid; i < T; i += K5_THREADS) {
+            double q = 0.0;
+            for (int d = 0; d < a.D; ++d) { const double g = ser[(size_t)d * a.Tld + i]; q += g * g; }
+            P[i + 1] = q;
+        }
+        if (tid == 0) P[0] = 0.0;
+        __syncthreads();
+        double run = 0.0;
+        for (int i = lo; i < hi; ++i) { run += P[i + 1]; P[i + 1] = run; }
+        double incl = run;   // inclusive scan of the segment totals over the block
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        double base = incl - run;
+        for (int w = 0; w < warp; ++w) base += wsum[w];
+        for (int i = lo; i < hi; ++i) P[i + 1] += base;
+        __syncthreads();
+        double* row = a.by_particle + (size_t)n * a.Tld;
+        const double tot = P[T];
+        for (int k = tid; k < T; k += K5_THREADS) {
+            double val = 0.0;                                   // lag 0 stays exactly 0 (viscosity.py:207-210)
+            if (k > 0) {
+                const double s1 = P[T - k] + (tot - P[k]);
+                val = (s1 / (double)(T - k) - 2.0 * row[k]) / (double)a.D / a.denom;
+            }
+            row[k] = val;
+            partial[k] += val;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // K4a: fixed-order sum of the per-CTA partial rows -> atom sum of this shard.
 // ---------------------------------------------------------------------------
 __global__ void k_sum_partials(const double* __restrict__ partial, int nrows, long long Tld, int T,

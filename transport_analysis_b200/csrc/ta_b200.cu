@@ -1022,6 +1022,43 @@ int ta_helfand(ta_ctx* ctx, const double* volumes, double boltzmann, double temp
     return finish_timeseries(ctx, grids, ts_out);
 }
 
+int ta_helfand_fft(ta_ctx* ctx, const double* volumes, double boltzmann, double temp_avg, double* ts_out) {
+    int rc = check_ready(ctx);
+    if (rc) return rc;
+    if (!ts_out || !volumes) return fail(ctx, TA_ERR_INVALID, "volumes / ts_out is null");
+    if (ctx->n_fields != 2) return fail(ctx, TA_ERR_INVALID, "ta_helfand_fft needs velocities and positions (n_fields == 2)");
+    if (ctx->precision != TA_PRECISION_FP64) return fail(ctx, TA_ERR_UNSUPPORTED, "the FFT route of the Helfand MSD is FP64 only");
+    double vsum = 0.0;
+    for (int64_t i = 0; i < ctx->T; ++i) vsum += volumes[i];
+    const double denom = 2 * boltzmann * (vsum / (double)ctx->T) * temp_avg;   // viscosity.py:205, :229-231
+    if ((rc = ensure_fft_plan(ctx))) return rc;
+    std::vector<int> grids;
+    rc = (ctx->fast_r1 > 0) ? launch_fft_fast(ctx, &grids) : launch_fft<double>(ctx, &grids);   // by_particle = sum_d acf_d
+    if (rc) return rc;
+    const size_t smem = ((size_t)ctx->T + 1) * sizeof(double);
+    for (size_t i = 0; i < ctx->sh.size(); ++i) {
+        Shard& s = ctx->sh[i];
+        if (s.natoms == 0) continue;
+        CK(cudaSetDevice(s.dev));
+        if (smem > (size_t)s.max_smem)
+            return fail(ctx, TA_ERR_UNSUPPORTED, "FFT Helfand route: T=" + std::to_string(ctx->T) + " does not fit shared memory");
+        CK(cudaFuncSetAttribute(k5_helfand_fft_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k5_helfand_fft_finish, K5_THREADS, smem));
+        if (occ < 1) return fail(ctx, TA_ERR_UNSUPPORTED, "K5 does not fit on an SM");
+        const int grid = (int)std::min<int64_t>(s.natoms, (int64_t)s.num_sms * occ);
+        grids[i] = grid;
+        if ((rc = ensure_partial(ctx, s, (size_t)grid))) return rc;    // drops K1's partial rows (sums of the ACF)
+        HelfandFftArgs a;
+        a.series = s.series; a.by_particle = s.by_particle; a.partial = s.partial;
+        a.natoms = (int)s.natoms; a.D = ctx->D; a.T = (int)ctx->T; a.Tld = ctx->Tld; a.denom = denom;
+        k5_helfand_fft_finish<<<grid, K5_THREADS, smem, s.s_compute>>>(a);
+        CK(cudaGetLastError());
+        ctx->launches++;
+    }
+    return finish_timeseries(ctx, grids, ts_out);
+}
+
 int ta_fetch_by_particle(ta_ctx* ctx, int64_t atom0, int64_t natoms, int layout, double* out) {
     if (!ctx || !ctx->begun) return fail(ctx, TA_ERR_INVALID, "ta_stage_begin has not been called");
     if (!out || atom0 < 0 || natoms < 0 || atom0 + natoms > ctx->N) return fail(ctx, TA_ERR_INVALID, "bad particle range");
