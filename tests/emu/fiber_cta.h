@@ -113,8 +113,16 @@ inline double shfl_xor(double v, int mask) {
     return got;
 }
 
+inline void sync_warp() {
+    Cta* c = active();
+    const int warp = c->current >> 5;
+    const int width = (c->nthreads - warp * 32) < 32 ? (c->nthreads - warp * 32) : 32;
+    sync_warp_internal(c, warp, width);
+}
+
 struct EmuCtx {
     static void sync() { sync_block(); }
+    static void sync_warp() { emu::sync_warp(); }
     static double shfl_xor16(double v) { return emu::shfl_xor(v, 16); }
     static double shfl_xor(double v, int mask) { return emu::shfl_xor(v, mask); }
     static void prefetch_l2(const void*, size_t, int, int) {}

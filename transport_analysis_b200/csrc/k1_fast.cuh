@@ -20,6 +20,11 @@
 //     lanes l and l ^ 16, so partner bins are exchanged with shuffles and the
 //     (Sigma, Delta) accumulators of a thread's 8 bin pairs stay in registers
 //     over the D series; the same exchange feeds the inverse.
+//   * P2 runs on the same warp as the P3 butterflies that consume its output (a warp owns the two
+//     256-point blocks k1 and R1-k1 -- r = 1: k1 and R1-1-k1 -- in both passes), so P2 -> P3 and
+//     P3' -> P2' need a warp-level sync only; the CTA barriers that remain are P1 -> P2, the
+//     buffer hand-over to the next series, and P2' -> P1'.  Warps drift apart inside the
+//     barrier-free stretch, which lets one warp's shared-memory traffic overlap another's math.
 //   * All butterflies are register DFTs with compile-time constants
 //     (dft_regs.cuh); P2 twiddles come from a 240-entry table, P1 twiddles are
 //     powers of one table entry per thread.
@@ -40,7 +45,7 @@ struct K1FArgs {
     double* partial;             // [grid][Tld]
     const cd* omega;             // [256]      w_{2H}^j
     const cd* tw2;               // [15][16]   w_256^{j k}, k = 1..15
-    const uint32_t* map;         // [2][16 R1] P3 butterfly of a thread, per residue (+ flags)
+    const uint32_t* map;         // [2][16 R1] per residue: bits 0-15 P3 butterfly of a thread, 16-23 its P2 block, 30/31 flags
     const cd* wbase;             // [2][16 R1] w_L^{2 G0 + r} of that butterfly
     const double* inv;           // [Tld]      1 / (L (T - k)), 0 beyond T
     int natoms, D, T, nh;
@@ -171,7 +176,8 @@ TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid,
                 for (int it = 0; it < NB; ++it) {
                     const int vt = tid + it * NT;
                     if (NV % NT != 0 && vt >= NV) break;
-                    const int p2base = (vt >> 4) * 272 + j2;     // padded address of (blk*256 + j), + 17 q
+                    const int blk2 = (int)((A.map[r * NV + vt] >> 16) & 0xffu);
+                    const int p2base = blk2 * 272 + j2;          // padded address of (blk*256 + j), + 17 q
                     cd x[16];
 #pragma unroll
                     for (int q = 0; q < 16; ++q) x[q] = buf[p2base + 17 * q];
@@ -183,7 +189,7 @@ TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid,
 #pragma unroll
                     for (int k = 0; k < 16; ++k) buf[p2base + 17 * k] = x[k];
                 }
-                Ctx::sync();
+                Ctx::sync_warp();        // P3 of this warp reads what this warp's P2 wrote
                 K1F_TICK(5, 0.0);
                 // ---------------- P3: radix 16, stride 1, + pair accumulation
                 static_for<0, NB>([&](auto iit) {
@@ -251,14 +257,15 @@ TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid,
 #pragma unroll
                 for (int q = 0; q < 16; ++q) buf[p3base + q] = v[q];
             });
-            Ctx::sync();
+            Ctx::sync_warp();
             K1F_TICK(10, 0.0);
             // ---------------- P2'
 #pragma unroll
             for (int it = 0; it < NB; ++it) {
                 const int vt = tid + it * NT;
                 if (NV % NT != 0 && vt >= NV) break;
-                const int p2base = (vt >> 4) * 272 + j2;
+                const int blk2 = (int)((A.map[r * NV + vt] >> 16) & 0xffu);
+                const int p2base = blk2 * 272 + j2;
                 cd x[16];
                 x[0] = buf[p2base];
 #pragma unroll
@@ -384,27 +391,30 @@ inline int k1f_build_plan(int64_t T, int64_t Tld, int R1, K1FastPlan* p) {
     const int NT = p->NT;
     p->map.assign(2 * (size_t)NT, 0);
     p->wbase.assign(4 * (size_t)NT, 0.0);
-    // residue 0: owner / partner butterflies (see DESIGN.md "K1 fast path")
+    // residue 0: owner / partner butterflies (see DESIGN.md "K1 fast path").  Pair index pidx = 16 w + i
+    // (warp w, i = lane & 15): warp 0 holds the two self-paired blocks k1 = 0 (i < 8) and k1 = R1/2
+    // (i >= 8), warp w >= 1 the blocks k1 = w (owners) and R1 - w (partners).
     std::vector<uint32_t> own(8 * R1), par(8 * R1);
-    int pi = 0;
-    for (int k2 = 0; k2 < 8; ++k2, ++pi) {
-        own[pi] = (uint32_t)k2 | (k2 == 0 ? K1F_SELF0 : 0u);
-        par[pi] = (k2 == 0) ? (8u | K1F_SELF8) : (uint32_t)(16 - k2);
+    for (int k2 = 0; k2 < 8; ++k2) {
+        own[k2] = (uint32_t)k2 | (k2 == 0 ? K1F_SELF0 : 0u);
+        par[k2] = (k2 == 0) ? (8u | K1F_SELF8) : (uint32_t)(16 - k2);
+        own[8 + k2] = (uint32_t)((R1 / 2) * 16 + k2);
+        par[8 + k2] = (uint32_t)((R1 / 2) * 16 + 15 - k2);
     }
     for (int k1 = 1; k1 < R1 / 2; ++k1)
-        for (int k2 = 0; k2 < 16; ++k2, ++pi) {
-            own[pi] = (uint32_t)(k1 * 16 + k2);
-            par[pi] = (uint32_t)((R1 - k1) * 16 + 15 - k2);
+        for (int k2 = 0; k2 < 16; ++k2) {
+            own[16 * k1 + k2] = (uint32_t)(k1 * 16 + k2);
+            par[16 * k1 + k2] = (uint32_t)((R1 - k1) * 16 + 15 - k2);
         }
-    for (int k2 = 0; k2 < 8; ++k2, ++pi) {
-        own[pi] = (uint32_t)((R1 / 2) * 16 + k2);
-        par[pi] = (uint32_t)((R1 / 2) * 16 + 15 - k2);
-    }
-    if (pi != 8 * R1) return TA_ERR_INVALID;
     for (int tid = 0; tid < NT; ++tid) {
         const int w = tid >> 5, l = tid & 31, pidx = w * 16 + (l & 15), side = l >> 4;
         p->map[tid] = side ? par[pidx] : own[pidx];
         p->map[NT + tid] = (uint32_t)(side ? (NT - 1 - pidx) : pidx);
+        // P2 block of this thread (one block per half-warp), the same two blocks the warp's P3 butterflies cover
+        const uint32_t blk2_r0 = (w == 0) ? (side ? (uint32_t)(R1 / 2) : 0u) : (side ? (uint32_t)(R1 - w) : (uint32_t)w);
+        const uint32_t blk2_r1 = side ? (uint32_t)(R1 - 1 - w) : (uint32_t)w;
+        p->map[tid] |= blk2_r0 << 16;
+        p->map[NT + tid] |= blk2_r1 << 16;
         for (int r = 0; r < 2; ++r) {
             const int blk3 = (int)(p->map[r * NT + tid] & 0xffffu);
             const int k1 = blk3 >> 4, k2 = blk3 & 15;

@@ -133,6 +133,11 @@ struct DevCtx {
         __syncthreads();
 #endif
     }
+    static TA_HD void sync_warp() {
+#if defined(__CUDA_ARCH__)
+        __syncwarp();
+#endif
+    }
     static TA_HD double shfl_xor(double v, int mask) {
 #if defined(__CUDA_ARCH__)
         return __shfl_xor_sync(0xffffffffu, v, mask);
