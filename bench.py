@@ -330,7 +330,8 @@ def run_b200(args, rank, world, local_rank):
             dev_ms.append(max_over_ranks(ms))
             k_ms.append(ctx.last_kernel_ms())
     launches = ctx.launch_count() - launches0
-    assert np.array_equal(ts, ts_e2e), "device-resident and end-to-end results differ"
+    # same per-particle values; the particle sum is associated per launch (one launch here, one per staging chunk in run())
+    assert np.allclose(ts, ts_e2e, rtol=1e-12, atol=1e-14 * np.abs(ts_e2e).max()), "device-resident and end-to-end results differ"
 
     ms_step = float(np.mean(dev_ms))
     af_total = float(A) * T * world
