@@ -68,6 +68,7 @@ static int run_win(const double* series, int T, int D, int Tld, int mode, int nw
     WinArgs a;
     a.series = series; a.by_particle = row.data(); a.partial = partial.data();
     a.natoms = 1; a.D = D; a.T = T; a.Tld = Tld; a.denom = 1.0;
+    a.scratch = nullptr; a.scratch_stride = 0;
     const int nthr = 32 * nwarps;
     if (mode == TA_WIN_PRODUCT) emu::run_cta(nthr, [&](int tid) { win_body<R, TA_WIN_PRODUCT, emu::EmuCtx>(a, sm, tid, nthr, 0, 1); });
     else emu::run_cta(nthr, [&](int tid) { win_body<R, TA_WIN_SQDIFF, emu::EmuCtx>(a, sm, tid, nthr, 0, 1); });

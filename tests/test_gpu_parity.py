@@ -368,3 +368,20 @@ def test_helfand_fft_route_general_kernel_and_window(rand_u, monkeypatch):
     assert_allclose(fast.results.timeseries, exact.results.timeseries, rtol=1e-7)
     assert_allclose(fast.results.viscosity, exact.results.viscosity, rtol=1e-8)
     assert_allclose(fast.running_viscosity, exact.running_viscosity, rtol=1e-7)
+
+
+# ------------------------------------------------------------------ series longer than shared memory (direct routes)
+def test_windowed_routes_beyond_shared_memory():
+    """T = 16,000 frames: series + lag sums of one particle (17 T bytes) exceed the 227 KB of an SM, so K2/K3
+    keep them in a per-CTA global scratch area instead; same arithmetic, same parity bar."""
+    T, N = 16000, 2
+    vel, pos = random_trajectory(T, N, seed=21, with_positions=True, rho=0.95)
+    masses = np.array([12.011, 1.008])
+    u = make_universe(pos, vel, masses=masses, dimensions=BOX)
+    w = VACF(u.atoms, dim_type="x", fft=False).run()
+    ref_bp, ref_ts = oracle.vacf_windowed(_f64(vel)[:, :, [0]])
+    assert_close_normwise(w.results.vacf_by_particle, ref_bp, TOL64)
+    assert_close_normwise(w.results.timeseries, ref_ts, TOL64)
+    h = VH(u.atoms, dim_type="x").run()
+    _, ref_h = oracle.helfand_msd(_f64(vel)[:, :, [0]], _f64(pos)[:, :, [0]], masses, np.full(T, np.prod(BOX[:3])), 300.0)
+    assert_allclose(h.results.timeseries, ref_h, rtol=TOL64)

@@ -215,11 +215,11 @@ k1f_fft_acf(const K1FArgs args) {
 // ---------------------------------------------------------------------------
 constexpr int KW_MAX_THREADS = 512;
 
-template <typename R, int MODE>
+template <typename R, int MODE, bool SCRATCH = false>
 __global__ void __launch_bounds__(KW_MAX_THREADS)
 k_windowed(const WinArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    win_body<R, MODE, DevCtx>(args, smem_raw, (int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x);
+    win_body<R, MODE, DevCtx, SCRATCH>(args, smem_raw, (int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // ---------------------------------------------------------------------------

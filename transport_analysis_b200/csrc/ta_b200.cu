@@ -107,6 +107,8 @@ struct Shard {
     double* lagmajor_tmp = nullptr;
     size_t lagmajor_bytes = 0;
     void* l2_scratch = nullptr;
+    void* win_scratch = nullptr;        // K2/K3 with T beyond shared memory: per-CTA series + lag sums
+    size_t win_scratch_bytes = 0;
     // FFT tables
     void* tw_lo = nullptr;
     void* tw_hi = nullptr;
@@ -185,6 +187,7 @@ void free_problem(ta_ctx* c) {
         cudaFree(s.ts_sum); s.ts_sum = nullptr;
         cudaFree(s.partial); s.partial = nullptr; s.partial_rows = 0;
         cudaFree(s.lagmajor_tmp); s.lagmajor_tmp = nullptr; s.lagmajor_bytes = 0;
+        cudaFree(s.win_scratch); s.win_scratch = nullptr; s.win_scratch_bytes = 0;
         for (int b = 0; b < kNumDevStage; ++b)
             for (int f = 0; f < 2; ++f) {
                 cudaFree(s.dstage[b][f]); s.dstage[b][f] = nullptr;
@@ -609,28 +612,40 @@ int launch_windowed(ta_ctx* ctx, double denom, std::vector<int>* grids) {
         Shard& s = ctx->sh[i];
         if (s.natoms == 0) continue;
         CK(cudaSetDevice(s.dev));
-        if (smem > (size_t)s.max_smem)
-            return fail(ctx, TA_ERR_UNSUPPORTED,
-                        "windowed route: T=" + std::to_string(T) + " needs " + std::to_string(smem) +
-                            " B of shared memory per CTA (limit " + std::to_string(s.max_smem) + ")");
-        CK(cudaFuncSetAttribute(k_windowed<R, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // series + lag sums of one particle: shared memory when they fit, else a per-CTA global scratch area
+        const bool in_smem = smem <= (size_t)s.max_smem;
+        const size_t dyn_smem = in_smem ? smem : 0;
+        if (in_smem) CK(cudaFuncSetAttribute(k_windowed<R, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_windowed<R, MODE>, nthr, smem));
+        if (in_smem) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_windowed<R, MODE, false>, nthr, dyn_smem));
+        else occ = 1;
         if (occ < 1) return fail(ctx, TA_ERR_UNSUPPORTED, "windowed kernel does not fit on an SM");
         int grid = (int)std::min<int64_t>(s.natoms, (int64_t)s.num_sms * occ);
+        if (!in_smem) {
+            const size_t need = smem * (size_t)grid;
+            if (s.win_scratch_bytes < need) {
+                cudaFree(s.win_scratch);
+                s.win_scratch = nullptr; s.win_scratch_bytes = 0;
+                CK(cudaMalloc(&s.win_scratch, need));
+                s.win_scratch_bytes = need;
+            }
+        }
         (*grids)[i] = grid;
         int rc = ensure_partial(ctx, s, (size_t)grid);
         if (rc) return rc;
         WinArgs a;
         a.partial = s.partial;
         a.D = ctx->D; a.T = T; a.Tld = ctx->Tld; a.denom = denom;
+        a.scratch = in_smem ? nullptr : (unsigned char*)s.win_scratch;
+        a.scratch_stride = (long long)smem;
         CK(cudaEventRecord(s.ev_ka, s.s_compute));
         for (const LaunchRange& rg : take_launch_ranges(s)) {
             if (rg.ready) CK(cudaStreamWaitEvent(s.s_compute, rg.ready, 0));
             a.series = s.series + (size_t)rg.a0 * ctx->D * ctx->Tld;
             a.by_particle = s.by_particle + (size_t)rg.a0 * ctx->Tld;
             a.natoms = (int)rg.n;
-            k_windowed<R, MODE><<<(int)std::min<int64_t>(grid, rg.n), nthr, smem, s.s_compute>>>(a);
+            if (in_smem) k_windowed<R, MODE, false><<<(int)std::min<int64_t>(grid, rg.n), nthr, dyn_smem, s.s_compute>>>(a);
+            else k_windowed<R, MODE, true><<<(int)std::min<int64_t>(grid, rg.n), nthr, 0, s.s_compute>>>(a);
             CK(cudaGetLastError());
             ctx->launches++;
         }

@@ -143,6 +143,10 @@ struct WinArgs {
     int natoms, D, T;
     long long Tld;
     double denom;           // Helfand: 2 kB <V> temp_avg ; VACF: unused
+    // Series too long for shared memory: per-CTA global scratch (same layout, read through L1/L2) -- slower,
+    // but the direct lag sums then work for any T.  Null: the series and the lag sums live in shared memory.
+    unsigned char* scratch;
+    long long scratch_stride;   // bytes per CTA
 };
 
 // ---------------------------------------------------------------------------
@@ -151,10 +155,11 @@ struct WinArgs {
 //   MODE = TA_WIN_PRODUCT: vacf[k] = sum_d sum_i g_d[i] g_d[i+k] / (T-k)
 //   MODE = TA_WIN_SQDIFF : visc[k] = sum_d sum_i (g_d[i]-g_d[i+k])^2 / (D (T-k)) / denom
 // ---------------------------------------------------------------------------
-template <typename R, int MODE, class Ctx>
+template <typename R, int MODE, class Ctx, bool SCRATCH = false>
 TA_HD void win_body(const WinArgs& A, unsigned char* smem_raw, int tid, int nthr, int bid, int nblk) {
     const int T = A.T;
     const int ne = win_smem_elems(T);
+    if (SCRATCH) smem_raw = A.scratch + (size_t)bid * (size_t)A.scratch_stride;   // compile-time: the shared-memory build keeps LDS/STS
     R* S = reinterpret_cast<R*>(smem_raw);
     double* res = reinterpret_cast<double*>(S + ((ne + 1) & ~1));
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
