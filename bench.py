@@ -129,6 +129,16 @@ def load_peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
+def k1_kernel_name(plan):
+    """Name of the K1 kernel the library picked, from the plan it reports (ta_fft_plan_info)."""
+    rad = plan["radices"]
+    if rad[1:] == [16, 16]:
+        return f"k1f_fft_acf<{rad[0]},{plan['threads']}> (K1 three-pass radix-16 path, bulk series prefetch)"
+    if rad[1:] == [8, 8, 8]:
+        return f"k1e_fft_acf<{rad[0]}> (K1 four-pass radix-8 path)"
+    return "k1_fft_acf<double> (K1 general mixed-radix kernel)"
+
+
 def load_profile_traffic(workload):
     """dram bytes per launch of the dominant kernel from the committed ncu summary."""
     path = os.path.join(ROOT, "profiles", "roofline_latest.json")
@@ -348,7 +358,7 @@ def run_b200(args, rank, world, local_rank):
         roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
                 "traffic": load_profile_traffic(workload),
-                "kernel": {"fft": "k1f_fft_acf<20,320> (K1 fast path)" if T > 7680 and T <= 10240 else "k1f_fft_acf / k1_fft_acf (K1)",
+                "kernel": {"fft": k1_kernel_name(ctx.fft_plan_info()) if workload == "fft" else "",
                            "windowed": "k_windowed<double,PRODUCT> (K2)",
                            "helfand": "k_windowed<double,SQDIFF> (K3)", "helfand_fft": "k1f_fft_acf (K1; K5 follows)"}[workload],
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": bytes_launch,

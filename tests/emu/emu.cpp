@@ -11,6 +11,7 @@
 #include "../../transport_analysis_b200/csrc/fft_core.cuh"
 #include "../../transport_analysis_b200/csrc/windowed_core.cuh"
 #include "../../transport_analysis_b200/csrc/k1_fast.cuh"
+#include "../../transport_analysis_b200/csrc/k1_r8.cuh"
 #include "fiber_cta.h"
 
 using namespace ta;
@@ -79,7 +80,7 @@ static int run_win(const double* series, int T, int D, int Tld, int mode, int nw
     return 0;
 }
 
-template <int R1>
+template <int R1, int VAR = 0>
 static int run_k1fast(const double* series, int T, int D, int Tld, int natoms, int nblk, double* by_particle,
                       double* partial) {
     K1FastPlan p;
@@ -93,15 +94,71 @@ static int run_k1fast(const double* series, int T, int D, int Tld, int natoms, i
     a.wbase = reinterpret_cast<const cd*>(p.wbase.data());
     a.inv = p.inv.data();
     a.natoms = natoms; a.D = D; a.T = T; a.nh = p.nh; a.Tld = Tld; a.prefetch = 0; a.stagger = 0; a.prof = nullptr;
-    std::vector<unsigned char> smem(k1f_smem_bytes(R1) + 64);
+    std::vector<unsigned char> smem(k1f_smem_bytes(R1, VAR) + 64);
     unsigned char* sm = smem.data() + (16 - ((uintptr_t)smem.data() & 15)) % 16;
     for (int bid = 0; bid < nblk; ++bid)
-        emu::run_cta(k1f_threads(R1), [&](int tid) { k1f_body<R1, k1f_threads(R1), emu::EmuCtx>(a, sm, tid, bid, nblk); });
+        emu::run_cta(k1f_threads(R1), [&](int tid) { k1f_body<R1, k1f_threads(R1), emu::EmuCtx, false, VAR>(a, sm, tid, bid, nblk); });
+    return 0;
+}
+
+template <int R>
+static int run_k1r8(const double* series, int T, int D, int Tld, int natoms, int nblk, double* by_particle, double* partial) {
+    K1R8Plan p;
+    int rc = k1e_build_plan(T, R, &p);
+    if (rc) return rc;
+    K1EArgs a;
+    a.series = series; a.by_particle = by_particle; a.partial = partial;
+    a.omega = reinterpret_cast<const cd*>(p.omega.data());
+    a.tw2 = reinterpret_cast<const cd*>(p.tw2.data());
+    a.tw3 = reinterpret_cast<const cd*>(p.tw3.data());
+    a.map = p.map.data();
+    a.wbase = reinterpret_cast<const cd*>(p.wbase.data());
+    a.natoms = natoms; a.D = D; a.T = T; a.nh = p.nh; a.Tld = Tld; a.sm_slots = nullptr; a.stagger = 0;
+    std::vector<unsigned char> smem(k1e_smem_bytes(R) + 64);
+    unsigned char* sm = smem.data() + (16 - ((uintptr_t)smem.data() & 15)) % 16;
+    for (int bid = 0; bid < nblk; ++bid)
+        emu::run_cta(k1e_threads(R), [&](int tid) { k1e_body<R, emu::EmuCtx>(a, sm, tid, bid, nblk); });
     return 0;
 }
 
 extern "C" {
+int emu_k1r8_r(int T) { return k1e_choose_r(T); }
+int emu_k1r8(const double* series, int T, int D, int Tld, int natoms, int nblk, int R, double* by_particle, double* partial) {
+    switch (R) {
+        case 4: return run_k1r8<4>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 5: return run_k1r8<5>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 6: return run_k1r8<6>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 8: return run_k1r8<8>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 10: return run_k1r8<10>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 12: return run_k1r8<12>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+    }
+    return -1;
+}
+// the plan's thread maps, for structural checks: returns NT, fills map[2 * NT]
+int emu_k1r8_map(int T, int R, unsigned* map) {
+    K1R8Plan p;
+    int rc = k1e_build_plan(T, R, &p);
+    if (rc) return rc;
+    for (size_t i = 0; i < p.map.size(); ++i) map[i] = p.map[i];
+    return p.NT;
+}
 int emu_k1fast_r1(int T) { return k1f_choose_r1(T); }
+// the experiment variants of the three-pass kernel (k1_fast.cuh VAR bits) at R1 = 20 and R1 = 10
+int emu_k1fast_var(const double* series, int T, int D, int Tld, int natoms, int nblk, int R1, int var, double* by_particle,
+                   double* partial) {
+    if (R1 == 20) switch (var) {
+        case 1: return run_k1fast<20, 1>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 2: return run_k1fast<20, 2>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 4: return run_k1fast<20, 4>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 6: return run_k1fast<20, 6>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+    }
+    if (R1 == 10) switch (var) {
+        case 2: return run_k1fast<10, 2>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 4: return run_k1fast<10, 4>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 6: return run_k1fast<10, 6>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+    }
+    return -1;
+}
 int emu_k1fast(const double* series, int T, int D, int Tld, int natoms, int nblk, int R1, double* by_particle,
                double* partial) {
     switch (R1) {

@@ -235,6 +235,7 @@ def test_lazy_by_particle(rand_u):
 def test_fft_fast_path_vs_oracle_and_general_kernel(T, N, dim, monkeypatch):
     """Every R1 instantiation of the three-pass kernel: against the oracle, and
     against the general mixed-radix kernel (TA_B200_FFT_GENERAL=1) on the same data."""
+    monkeypatch.setenv("TA_B200_K1_PATH", "r16")
     vel, _ = random_trajectory(T, N, seed=T + N, rho=0.8)
     u = make_universe(None, vel)
     cols, _ = oracle.parse_dim_type(dim)
@@ -250,8 +251,75 @@ def test_fft_fast_path_vs_oracle_and_general_kernel(T, N, dim, monkeypatch):
     assert_close_normwise(g.results.vacf_by_particle, v.results.vacf_by_particle, 1e-11, "fast vs general kernel")
 
 
-def test_fft_fast_path_ramp_known_answer():
+# ------------------------------------------------------------------ K1 radix-8 path (H = 512 R, k1_r8.cuh)
+@pytest.mark.parametrize("T,N,dim", [(3100, 5, "xyz"), (4000, 70, "xyz"), (4096, 3, "x"), (5000, 333, "xyz"), (5001, 2, "xy"),
+                                     (6000, 9, "yz"), (7000, 3, "z"), (8192, 2, "xyz"), (9999, 4, "xz"),
+                                     (10000, 301, "xyz"), (10240, 1, "xyz"), (12000, 5, "xyz")])
+def test_fft_radix8_path_vs_oracle_and_other_kernels(T, N, dim, monkeypatch):
+    """Every R instantiation of the four-pass radix-8 kernel: against the oracle, against the general mixed-radix
+    kernel and, where it has an instantiation, the three-pass radix-16 kernel.
+    N > 148 makes CTAs take several particles (staging-buffer hand-over, bulk reduce into the partial row)."""
+    monkeypatch.setenv("TA_B200_K1_PATH", "r8")
+    vel, _ = random_trajectory(T, N, seed=T + N, rho=0.8)
+    u = make_universe(None, vel)
+    cols, _ = oracle.parse_dim_type(dim)
+    v = VACF(u.atoms, dim_type=dim, fft=True).run()
+    plan = v._ctx.fft_plan_info()
+    assert plan["radices"][1:] == [8, 8, 8] and plan["H"] == 512 * plan["radices"][0], plan
+    n_or = min(N, 6)                                   # the oracle is a Python loop over particles
+    ref_bp, _ = oracle.vacf_fft(_f64(vel)[:, :n_or, cols])
+    assert_close_normwise(v.results.vacf_by_particle[:, :n_or], ref_bp, TOL64, "radix-8 vs oracle, by particle")
+    assert_close_normwise(v.results.timeseries, v.results.vacf_by_particle.mean(axis=1), 1e-13, "timeseries = particle mean")
+    again = VACF(u.atoms, dim_type=dim, fft=True).run()
+    assert np.array_equal(again.results.timeseries, v.results.timeseries)          # bit-reproducible
+    assert np.array_equal(again.results.vacf_by_particle, v.results.vacf_by_particle)
+    for path in ("general", "r16"):
+        monkeypatch.setenv("TA_B200_K1_PATH", path)
+        g = VACF(u.atoms, dim_type=dim, fft=True).run()
+        if path == "r16" and g._ctx.fft_plan_info()["radices"][1:] != [16, 16]:
+            continue
+        assert g._ctx.fft_plan_info()["smem_bytes"] != plan["smem_bytes"]        # a different kernel served the call
+        assert_close_normwise(g.results.vacf_by_particle, v.results.vacf_by_particle, 1e-11, f"radix-8 vs {path}")
+        assert_close_normwise(g.results.timeseries, v.results.timeseries, 1e-11, f"radix-8 vs {path}, timeseries")
+
+
+@pytest.mark.parametrize("T,want", [(1000, None), (2000, [4, 16, 16]), (5000, [10, 16, 16]), (10000, [20, 16, 16]),
+                                    (12000, [12, 8, 8, 8]), (13000, None)])
+def test_fft_default_kernel_choice(T, want):
+    """Three-pass radix-16 path where it has an instantiation, radix-8 path above it (T <= 12,288), else the general kernel."""
+    vel, _ = random_trajectory(T, 2, seed=T, rho=0.5)
+    v = VACF(make_universe(None, vel).atoms, fft=True).run()
+    rad = v._ctx.fft_plan_info()["radices"]
+    if want is None:
+        assert not (len(rad) == 3 and rad[1:] == [16, 16]) and not (len(rad) == 4 and rad[1:] == [8, 8, 8]), rad
+    else:
+        assert rad == want, rad
+    ref_bp, ref_ts = oracle.vacf_fft(_f64(vel))
+    assert_close_normwise(v.results.vacf_by_particle, ref_bp, TOL64, f"T={T}")
+    assert_close_normwise(v.results.timeseries, ref_ts, TOL64, f"T={T}")
+
+
+@pytest.mark.parametrize("var", [0, 1, 2, 3, 4, 5])
+def test_fft_three_pass_kernel_variants(var, monkeypatch):
+    """k1_fast.cuh VAR bits at R1 = 20 (token-ordered loads, staged bulk output, bulk series prefetch = the default):
+    same results whichever way the data moves.  N > 148 makes CTAs take several particles."""
+    T, N = 10000, 301
+    vel, _ = random_trajectory(T, N, seed=var, rho=0.7)
+    u = make_universe(None, vel)
+    monkeypatch.setenv("TA_B200_K1F_VAR", str(var))
+    v = VACF(u.atoms, fft=True).run()
+    assert v._ctx.fft_plan_info()["radices"] == [20, 16, 16]
+    ref_bp, _ = oracle.vacf_fft(_f64(vel)[:, :4])
+    assert_close_normwise(v.results.vacf_by_particle[:, :4], ref_bp, TOL64, f"variant {var} vs oracle")
+    assert_close_normwise(v.results.timeseries, v.results.vacf_by_particle.mean(axis=1), 1e-13, "timeseries = particle mean")
+    again = VACF(u.atoms, fft=True).run()
+    assert np.array_equal(again.results.timeseries, v.results.timeseries)
+    assert np.array_equal(again.results.vacf_by_particle, v.results.vacf_by_particle)
+
+
+def test_fft_fast_path_ramp_known_answer(monkeypatch):
     """The reference's step trajectory (v = t, 5001 frames) takes the fast path (R1 = 10)."""
+    monkeypatch.setenv("TA_B200_K1_PATH", "r16")
     t = np.arange(5001, dtype=np.float64)
     v = np.repeat(t[:, None, None], 3, axis=2)
     u = make_universe(None, v)
@@ -260,6 +328,11 @@ def test_fft_fast_path_ramp_known_answer():
     poly = oracle.characteristic_poly(5001, 3)
     assert_almost_equal(a.results.timeseries, poly, decimal=3)     # the reference's own bar (tests :454-469)
     assert_close_normwise(a.results.timeseries, poly, TOL64)
+    monkeypatch.setenv("TA_B200_K1_PATH", "r8")
+    b = VACF(u.atoms, fft=True).run()
+    assert b._ctx.fft_plan_info()["radices"] == [5, 8, 8, 8]
+    assert_almost_equal(b.results.timeseries, poly, decimal=3)
+    assert_close_normwise(b.results.timeseries, poly, TOL64)
 
 
 # ------------------------------------------------------------------ size-independent properties at BASELINE sizes

@@ -58,7 +58,9 @@ struct K1FArgs {
 constexpr uint32_t K1F_SELF0 = 1u << 30;   // butterfly holding g = 0 (pairs k <-> 16-k in-thread)
 constexpr uint32_t K1F_SELF8 = 1u << 31;   // butterfly holding g = H/2 (pairs k <-> 15-k in-thread)
 
-constexpr int k1f_smem_bytes(int R1) { return (256 * R1 + 16 * R1 + 256 + 240) * (int)sizeof(cd); }
+constexpr int k1f_smem_bytes(int R1, int VAR = 0) {
+    return (256 * R1 + 16 * R1 + 256 + 240 + ((VAR & 2) ? 256 * R1 : 0) + ((VAR & 4) ? 256 * R1 + 1 : 0)) * (int)sizeof(cd);
+}
 // Threads per CTA (NT) and resident CTAs per SM the kernel is compiled for.  A pass has NV = 16 R1
 // radix-16 butterflies; a thread owns the butterflies vt = tid, tid + NT, ... (whole warps, so the
 // lane exchange of P3 stays inside a warp).  Default: one butterfly per thread (NT = NV).
@@ -96,22 +98,73 @@ TA_HD void k1f_p1_twiddles(cd om, int r, cd* e, cd* g) {
 // device these are __syncthreads / __shfl_xor_sync, in tests/emu they are
 // cooperative-fiber versions so the very same code runs on the CPU.
 // ---------------------------------------------------------------------------
-template <int R1, int NT, class Ctx, bool PROF = false>
+// VAR bits (experiments; 0 = the measured default):
+//   1  token-ordered shared-memory / global load phases after a CTA barrier: the warps of one SM sub-partition
+//      (w, w + 4, w + 8) issue their loads one rank after the other instead of all at once, so rank 0 is already
+//      on the FP64 pipe while the LSU serves rank 1
+//   2  staged output: V_0 waits in a second shared buffer instead of the global row, the finished row is
+//      normalised with a computed 1 / (L (T - k)) and leaves the SM as one bulk (TMA) store of the per-particle
+//      row plus one bulk reduce-add into the per-CTA partial row, issued by a warp that is idle in P1':
+//      no parked-row / table / partial-row loads and no L2 round trips in the output phase
+//   4  series prefetch: while a chain runs P2 / P3, the bulk-copy engine (TMA) brings the next chain's series into a
+//      second shared buffer (one mbarrier, phase per chain), so P1 is a shared -> registers -> shared pass like the
+//      others and no warp waits for L2 / HBM
+constexpr int K1F_VAR_TURNS = 1;
+constexpr int K1F_VAR_STAGED = 2;
+constexpr int K1F_VAR_PREFETCH = 4;
+
+// Rank r (warps 4r .. 4r+3 of the first NW warps) may issue its loads once rank r-1 has issued its own.
+// Named barriers id0 + r; consecutive uses of one site are separated by a CTA barrier.
+template <class Ctx, int NW>
+TA_HD void k1f_turn_wait(int warp, int id0) {
+    const int rank = warp >> 2;
+    if (rank > 0 && warp < NW) {
+        const int prev = 4, cur = (NW - 4 * rank) < 4 ? (NW - 4 * rank) : 4;
+        Ctx::bar_sync(id0 + rank, 32 * (prev + cur));
+    }
+}
+template <class Ctx, int NW>
+TA_HD void k1f_turn_pass(int warp, int id0) {
+    const int rank = warp >> 2;
+    if (warp < NW && 4 * (rank + 1) < NW) {
+        const int nxt = (NW - 4 * (rank + 1)) < 4 ? (NW - 4 * (rank + 1)) : 4;
+        Ctx::bar_arrive(id0 + rank + 1, 32 * (4 + nxt));
+    }
+}
+
+template <int R1, int NT, class Ctx, bool PROF = false, int VAR = 0>
 TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid, int nblk) {
     constexpr int H = 256 * R1;
     constexpr int NV = 16 * R1;          // radix-16 butterflies per pass ("virtual threads")
     constexpr int NB = (NV + NT - 1) / NT;   // butterfly rounds of P2 / P3; a thread owns vt = tid + it NT < NV
     constexpr int NG = (R1 + 3) / 4;
     static_assert(NT % 32 == 0 && NV % 32 == 0, "the lane exchange needs whole warps");
+    constexpr bool TURNS = (VAR & K1F_VAR_TURNS) != 0 && NT == NV && NT >= 256;   // one butterfly per thread, >= 2 ranks
+    constexpr int NW = NT / 32, NW1 = 256 / 32;                                     // warps of P2 / P3 and of P1 / P1'
+    const int warp = tid >> 5;
     cd* buf = reinterpret_cast<cd*>(smem_raw);       // H + H/16 elements, padded layout
     cd* s_om = buf + (H + H / 16);                   // 256
     cd* s_tw2 = s_om + 256;                          // 240
+    cd* stg = s_tw2 + 240;                           // STAGED: H elements, plain layout (V_0, then the finished row)
+    constexpr bool STAGED = (VAR & K1F_VAR_STAGED) != 0;
+    constexpr bool PREF = (VAR & K1F_VAR_PREFETCH) != 0;
+    cd* pre = stg + (STAGED ? H : 0);                // PREF: H elements, the series of the coming chain as it lies in HBM
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(pre + H);   // PREF: "series has landed"
+    unsigned pre_phase = 0;
+    // the warp that issues the bulk store / reduce of a finished row: the last one, idle in P1' when NT > 256
+    constexpr int NPART = NT < 256 ? NT : 256;       // threads that take part in P1'
+    constexpr int WISS = NT / 32 - 1;
+    constexpr bool ISS_IDLE = NT > 256;
+    const double Ld = (double)(4 * H);
 
     for (int i = tid; i < 256; i += NT) s_om[i] = A.omega[i];
     for (int i = tid; i < 240; i += NT) s_tw2[i] = A.tw2[i];
+    if (PREF && tid == 0) Ctx::mbar_init(mbar);
     Ctx::sync();
 
     const int nh = A.nh;
+    const unsigned ser_bytes = (unsigned)nh * (unsigned)sizeof(cd);
+    if (PREF && tid == 0 && bid < A.natoms) Ctx::bulk_load(pre, A.series + (size_t)bid * A.D * A.Tld, ser_bytes, mbar);
     const int j2 = tid & 15;                         // NT is a multiple of 16: the same for every owned butterfly
     cd* part = reinterpret_cast<cd*>(A.partial + (size_t)bid * A.Tld);
     const cd* inv2 = reinterpret_cast<const cd*>(A.inv);
@@ -142,11 +195,22 @@ TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid,
                 const cd* src = reinterpret_cast<const cd*>(ser + (size_t)d * A.Tld);
                 for (int j = tid; j < 256; j += NT) {
                     cd x[R1];
+                    if (TURNS) k1f_turn_wait<Ctx, NW1>(warp, 1);
+                    if (PREF) {
+                        if (j == tid) Ctx::mbar_wait(mbar, pre_phase);
 #pragma unroll
-                    for (int q = 0; q < R1; ++q) {
-                        const int n = j + 256 * q;
-                        x[q] = (n < nh) ? Ctx::ld_stream(src + n) : cmake<double>(0.0, 0.0);
+                        for (int q = 0; q < R1; ++q) {
+                            const int n = j + 256 * q;
+                            x[q] = (n < nh) ? pre[n] : cmake<double>(0.0, 0.0);
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < R1; ++q) {
+                            const int n = j + 256 * q;
+                            x[q] = (n < nh) ? Ctx::ld_stream(src + n) : cmake<double>(0.0, 0.0);
+                        }
                     }
+                    if (TURNS) k1f_turn_pass<Ctx, NW1>(warp, 1);
                     K1F_TICK(0, x[R1 - 1].y + x[0].x);
                     if (r) {
                         static_for<1, R1>([&](auto iq) {
@@ -170,6 +234,17 @@ TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid,
                     for (int k = 0; k < R1; ++k) dst[272 * k] = x[k];
                 }
                 Ctx::sync();
+                if (PREF) {
+                    // every P1 thread has read the prefetch buffer: hand it to the bulk-copy engine for the next chain
+                    pre_phase ^= 1u;
+                    if (tid == NT - 1) {
+                        const double* nxt = nullptr;
+                        if (d + 1 < A.D) nxt = ser + (size_t)(d + 1) * A.Tld;
+                        else if (r == 0) nxt = ser;
+                        else if (atom + nblk < A.natoms) nxt = ser + (size_t)nblk * A.D * A.Tld;
+                        if (nxt) Ctx::bulk_load(pre, nxt, ser_bytes, mbar);
+                    }
+                }
                 K1F_TICK(2, 0.0);
                 // ---------------- P2: radix 16, stride 16
 #pragma unroll
@@ -179,8 +254,10 @@ TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid,
                     const int blk2 = (int)((A.map[r * NV + vt] >> 16) & 0xffu);
                     const int p2base = blk2 * 272 + j2;          // padded address of (blk*256 + j), + 17 q
                     cd x[16];
+                    if (TURNS) k1f_turn_wait<Ctx, NW>(warp, 4);
 #pragma unroll
                     for (int q = 0; q < 16; ++q) x[q] = buf[p2base + 17 * q];
+                    if (TURNS) k1f_turn_pass<Ctx, NW>(warp, 4);
                     K1F_TICK(3, x[15].y + x[0].x);
                     Dft<16, -1>::run(x);
 #pragma unroll
@@ -275,6 +352,8 @@ TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid,
 #pragma unroll
                 for (int q = 0; q < 16; ++q) buf[p2base + 17 * q] = x[q];
             }
+            // STAGED: the bulk operations of the previous particle have read (and reduced) the staging buffer
+            if (STAGED && tid == 32 * WISS) Ctx::bulk_wait_all();
             Ctx::sync();
             K1F_TICK(12, 0.0);
             // ---------------- P1' + output
@@ -283,9 +362,13 @@ TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid,
                 k1f_p1_twiddles<R1>(s_om[j], r, e, g);
                 const cd* srcb = buf + j + (j >> 4);
                 cd x[R1];
+                if (TURNS) k1f_turn_wait<Ctx, NW1>(warp, 7);
+#pragma unroll
+                for (int k = 0; k < R1; ++k) x[k] = srcb[272 * k];
+                if (TURNS) k1f_turn_pass<Ctx, NW1>(warp, 7);
 #pragma unroll
                 for (int k = 0; k < R1; ++k) {
-                    cd y = srcb[272 * k];
+                    cd y = x[k];
                     if (k >= 4) y = cmulc(y, g[k >> 2]);
                     if (r || (k & 3)) y = cmulc(y, e[k & 3]);
                     x[k] = y;
@@ -299,7 +382,22 @@ TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid,
                 }
                 // x[q] = V_r[n] (r = 1: already multiplied by conj(w_L^{2n})), n = j + 256 q
                 K1F_TICK(13, x[R1 - 1].y + x[0].x);
-                if (r == 0) {
+                if (STAGED) {
+                    if (r == 0) {
+#pragma unroll
+                        for (int q = 0; q < R1; ++q) stg[j + 256 * q] = x[q];     // V_0 waits here for residue 1
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < R1; ++q) {
+                            const int n = j + 256 * q;
+                            const int k = 2 * n;
+                            const cd v0 = stg[n];
+                            const double sx = k < A.T ? Ctx::rcp(Ld * (double)(A.T - k)) : 0.0;
+                            const double sy = k + 1 < A.T ? Ctx::rcp(Ld * (double)(A.T - k - 1)) : 0.0;
+                            stg[n] = cmake<double>((v0.x + x[q].x) * sx, (v0.y + x[q].y) * sy);
+                        }
+                    }
+                } else if (r == 0) {
 #pragma unroll
                     for (int q = 0; q < R1; ++q) {
                         const int n = j + 256 * q;
@@ -338,11 +436,29 @@ TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid,
                     });
                 }
             }
+            if (STAGED && r == 1) {
+                // every P1' thread has written its part of the finished row -> one warp hands it to the
+                // bulk-copy engine: row store + reduce-add into this CTA's partial row (fixed order:
+                // the previous particle's group has completed, see bulk_wait_all above)
+                const unsigned nbytes = (unsigned)nh * (unsigned)sizeof(cd);
+                if (ISS_IDLE) {
+                    if (tid < NPART) { Ctx::fence_async_smem(); Ctx::bar_arrive(10, NPART + 32); }
+                    else if ((tid >> 5) == WISS) {
+                        Ctx::bar_sync(10, NPART + 32);
+                        if (tid == 32 * WISS) Ctx::bulk_store_and_add(row, part, stg, nbytes);
+                    }
+                } else {
+                    Ctx::fence_async_smem();
+                    Ctx::sync();
+                    if (tid == 32 * WISS) Ctx::bulk_store_and_add(row, part, stg, nbytes);
+                }
+            }
             // no barrier here: P1 of the next chain writes exactly the elements this
             // thread has just read in P1'
             K1F_TICK(14, 0.0);
         }
     }
+    if (STAGED && tid == 32 * WISS) Ctx::bulk_wait_all();
 #undef K1F_TICK
 }
 

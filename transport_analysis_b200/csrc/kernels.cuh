@@ -9,6 +9,7 @@
 #include "fft_core.cuh"
 #include "windowed_core.cuh"
 #include "k1_fast.cuh"
+#include "k1_r8.cuh"
 
 namespace ta {
 
@@ -166,6 +167,78 @@ struct DevCtx {
         asm volatile("" ::: "memory");
 #endif
     }
+    // named barriers (ids 1..15; id 0 is __syncthreads): wait for / signal `count` threads
+    static TA_HD void bar_sync(int id, int count) {
+#if defined(__CUDA_ARCH__)
+        asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+#endif
+    }
+    static TA_HD void bar_arrive(int id, int count) {
+#if defined(__CUDA_ARCH__)
+        asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+#endif
+    }
+    // 1 / a for a > 0: hardware seed + two Newton steps (within 1 ulp; no table, no division sequence)
+    static TA_HD double rcp(double a) {
+#if defined(__CUDA_ARCH__)
+        double y;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+        double e = fma(-a, y, 1.0);
+        y = fma(y, e, y);
+        e = fma(-a, y, 1.0);
+        return fma(y, e, y);
+#else
+        return 1.0 / a;
+#endif
+    }
+    // shared-memory writes of this thread become visible to the bulk-copy (async) proxy
+    static TA_HD void fence_async_smem() {
+#if defined(__CUDA_ARCH__)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+    }
+    // one bulk group: row[0..bytes) = src, part[0..bytes) += src (f64 reduce-add at L2); src is shared memory
+    static TA_HD void bulk_store_and_add(cd* row, cd* part, const cd* src, unsigned bytes) {
+#if defined(__CUDA_ARCH__)
+        const unsigned s = (unsigned)__cvta_generic_to_shared(src);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(row), "r"(s), "r"(bytes) : "memory");
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(part), "r"(s), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#endif
+    }
+    // mbarrier with one arrival per phase (the thread that issues the bulk load)
+    static TA_HD void mbar_init(unsigned long long* bar) {
+#if defined(__CUDA_ARCH__)
+        const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+    }
+    // dst[0..bytes) (shared) <- src (global) by the bulk-copy engine; completion flips the phase of `bar`
+    static TA_HD void bulk_load(cd* dst, const double* src, unsigned bytes, unsigned long long* bar) {
+#if defined(__CUDA_ARCH__)
+        const unsigned a = (unsigned)__cvta_generic_to_shared(bar), d = (unsigned)__cvta_generic_to_shared(dst);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(d), "l"(src), "r"(bytes), "r"(a) : "memory");
+#endif
+    }
+    static TA_HD void mbar_wait(unsigned long long* bar, unsigned parity) {
+#if defined(__CUDA_ARCH__)
+        const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+        unsigned done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        }
+#endif
+    }
+    // all bulk groups of this thread have completed (source read and destination written)
+    static TA_HD void bulk_wait_all() {
+#if defined(__CUDA_ARCH__)
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#endif
+    }
     static TA_HD long long clock_after(double dep) {
 #if defined(__CUDA_ARCH__)
         long long t;
@@ -179,6 +252,23 @@ struct DevCtx {
 #if defined(__CUDA_ARCH__)
         const long long t0 = clock64();
         while (clock64() - t0 < clocks) {}
+        __syncthreads();
+#endif
+    }
+    // the CTA that arrives second (fourth, ...) on its SM idles for `clocks` before it starts
+    static TA_HD void stagger_second_cta(unsigned* sm_slots, int clocks, int tid) {
+#if defined(__CUDA_ARCH__)
+        __shared__ unsigned s_slot;
+        if (tid == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            s_slot = atomicAdd(sm_slots + smid, 1u);
+        }
+        __syncthreads();
+        if (s_slot & 1u) {
+            const long long t0 = clock64();
+            while (clock64() - t0 < clocks) {}
+        }
         __syncthreads();
 #endif
     }
@@ -201,11 +291,21 @@ struct DevCtx {
     }
 };
 
-template <int R1, int NT, bool PROF = false>
+template <int R1, int NT, bool PROF = false, int VAR = 0>
 __global__ void __launch_bounds__(NT, k1f_min_blocks(NT))
 k1f_fft_acf(const K1FArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    k1f_body<R1, NT, DevCtx, PROF>(args, smem_raw, (int)threadIdx.x, (int)blockIdx.x, (int)gridDim.x);
+    k1f_body<R1, NT, DevCtx, PROF, VAR>(args, smem_raw, (int)threadIdx.x, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// ---------------------------------------------------------------------------
+// K1 radix-8 path (k1_r8.cuh): H = 512 R in four passes, 64 R threads, one CTA per SM.
+// ---------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(64 * R, R <= 5 ? 2 : 1)
+k1e_fft_acf(const K1EArgs args) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    k1e_body<R, DevCtx>(args, smem_raw, (int)threadIdx.x, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // ---------------------------------------------------------------------------

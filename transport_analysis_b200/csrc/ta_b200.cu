@@ -121,6 +121,13 @@ struct Shard {
     uint32_t* f_map = nullptr;
     void* f_wbase = nullptr;
     double* f_inv = nullptr;
+    // radix-8 path FFT tables (k1_r8.cuh)
+    void* e_omega = nullptr;
+    void* e_tw2 = nullptr;
+    void* e_tw3 = nullptr;
+    uint32_t* e_map = nullptr;
+    void* e_wbase = nullptr;
+    unsigned* e_slots = nullptr;        // [1024] per-SM CTA arrival counters (stagger of co-resident CTAs)
 };
 
 }  // namespace
@@ -148,7 +155,8 @@ struct ta_ctx {
     int64_t plan_T = -1;
     int plan_prec = -1;
     int npairs0 = 0;
-    int fast_r1 = 0;         // > 0: the plan is for the fast path with this R1
+    int fast_r1 = 0;         // > 0: the plan is for the three-pass path (k1_fast.cuh) with this R1
+    int fast_r8 = 0;         // > 0: the plan is for the radix-8 path (k1_r8.cuh) with this R
     int k1_threads = 0, k1_smem = 0, k1_grid = 0;
     std::vector<double> host_ts;
     int64_t launches = 0;
@@ -207,6 +215,12 @@ void free_problem(ta_ctx* c) {
         cudaFree(s.f_map); s.f_map = nullptr;
         cudaFree(s.f_wbase); s.f_wbase = nullptr;
         cudaFree(s.f_inv); s.f_inv = nullptr;
+        cudaFree(s.e_omega); s.e_omega = nullptr;
+        cudaFree(s.e_tw2); s.e_tw2 = nullptr;
+        cudaFree(s.e_tw3); s.e_tw3 = nullptr;
+        cudaFree(s.e_map); s.e_map = nullptr;
+        cudaFree(s.e_wbase); s.e_wbase = nullptr;
+        cudaFree(s.e_slots); s.e_slots = nullptr;
     }
     for (int i = 0; i < kNumSlabs; ++i) {
         if (c->slab[i]) cudaFreeHost(c->slab[i]);
@@ -426,12 +440,52 @@ int upload_fast_tables(ta_ctx* ctx, const K1FastPlan& p) {
     return TA_OK;
 }
 
+int upload_r8_tables(ta_ctx* ctx, const K1R8Plan& p) {
+    for (auto& s : ctx->sh) {
+        CK(cudaSetDevice(s.dev));
+        cudaFree(s.e_omega); cudaFree(s.e_tw2); cudaFree(s.e_tw3); cudaFree(s.e_map); cudaFree(s.e_wbase);
+        s.e_omega = s.e_tw2 = s.e_tw3 = s.e_wbase = nullptr; s.e_map = nullptr;
+#define TA_UP(dst, vec)                                                                         \
+        CK(cudaMalloc((void**)&dst, vec.size() * sizeof(vec[0])));                              \
+        CK(cudaMemcpy(dst, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice));
+        TA_UP(s.e_omega, p.omega);
+        TA_UP(s.e_tw2, p.tw2);
+        TA_UP(s.e_tw3, p.tw3);
+        TA_UP(s.e_map, p.map);
+        TA_UP(s.e_wbase, p.wbase);
+#undef TA_UP
+        if (!s.e_slots) CK(cudaMalloc((void**)&s.e_slots, 1024 * sizeof(unsigned)));
+    }
+    return TA_OK;
+}
+
+// Which K1 kernel serves T (FP64): the three-pass radix-16 path where it has an instantiation (the faster of the two
+// wherever both exist: 24.2 against 27.4 ms at 100k x 10k, 23.6 against 25.5 ms at 200k x 5k), else the four-pass radix-8
+// path (T up to 12,288), else the general kernel.  TA_B200_K1_PATH = r16 | r8 | general restricts the choice
+// (experiments and the tests that compare the kernels with each other).
+int plan_r8(ta_ctx* ctx, int r8) {
+    K1R8Plan ep;
+    int rce = k1e_build_plan(ctx->T, r8, &ep);
+    if (rce) return fail(ctx, rce, "cannot plan the radix-8 FFT path for T=" + std::to_string(ctx->T));
+    if ((rce = upload_r8_tables(ctx, ep))) return rce;
+    ctx->fast_r8 = r8;
+    ctx->plan.H = ep.H; ctx->plan.L = ep.L; ctx->plan.npasses = 4;
+    ctx->plan.radix[0] = r8; ctx->plan.radix[1] = 8; ctx->plan.radix[2] = 8; ctx->plan.radix[3] = 8;
+    ctx->plan_T = ctx->T;
+    ctx->plan_prec = ctx->precision;
+    return TA_OK;
+}
+
 int ensure_fft_plan(ta_ctx* ctx) {
     if (ctx->plan_T == ctx->T && ctx->plan_prec == ctx->precision) return TA_OK;
     ctx->fast_r1 = 0;
+    ctx->fast_r8 = 0;
     const char* force_general = getenv("TA_B200_FFT_GENERAL");
-    const int r1 = (ctx->precision == TA_PRECISION_FP64 && !(force_general && force_general[0] == '1'))
-                       ? k1f_choose_r1(ctx->T) : 0;
+    const char* path = getenv("TA_B200_K1_PATH");
+    const std::string want = (force_general && force_general[0] == '1') ? "general" : (path ? path : "");
+    const bool fp64 = ctx->precision == TA_PRECISION_FP64;
+    if (fp64 && want == "r8" && k1e_choose_r(ctx->T) > 0) return plan_r8(ctx, k1e_choose_r(ctx->T));
+    const int r1 = (fp64 && (want.empty() || want == "r16")) ? k1f_choose_r1(ctx->T) : 0;
     if (r1 > 0) {
         K1FastPlan fp;
         int rcf = k1f_build_plan(ctx->T, ctx->Tld, r1, &fp);
@@ -444,6 +498,7 @@ int ensure_fft_plan(ta_ctx* ctx) {
         ctx->plan_prec = ctx->precision;
         return TA_OK;
     }
+    if (fp64 && want.empty() && k1e_choose_r(ctx->T) > 0) return plan_r8(ctx, k1e_choose_r(ctx->T));
     int rc = ta_build_fft_plan(ctx->T, &ctx->plan);
     if (rc) return fail(ctx, rc, "cannot plan an FFT for T=" + std::to_string(ctx->T));
     std::vector<uint32_t> own0;
@@ -517,18 +572,18 @@ int env_int(const char* name, int dflt) {
     return (v && v[0]) ? atoi(v) : dflt;
 }
 
-template <int R1, int NT, bool PROF = false>
+template <int R1, int NT, bool PROF = false, int VAR = 0>
 int launch_fft_fast_r1(ta_ctx* ctx, std::vector<int>* grids) {
-    const int smem = k1f_smem_bytes(R1);
+    const int smem = k1f_smem_bytes(R1, VAR);
     const int nthr = NT;
     grids->assign(ctx->sh.size(), 0);
     for (size_t i = 0; i < ctx->sh.size(); ++i) {
         Shard& s = ctx->sh[i];
         if (s.natoms == 0) continue;
         CK(cudaSetDevice(s.dev));
-        CK(cudaFuncSetAttribute(k1f_fft_acf<R1, NT, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(k1f_fft_acf<R1, NT, PROF, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1f_fft_acf<R1, NT, PROF>, nthr, (size_t)smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1f_fft_acf<R1, NT, PROF, VAR>, nthr, (size_t)smem));
         if (occ < 1) return fail(ctx, TA_ERR_UNSUPPORTED, "fast FFT kernel does not fit on an SM");
         int grid = (int)std::min<int64_t>(s.natoms, (int64_t)s.num_sms * occ);
         (*grids)[i] = grid;
@@ -553,7 +608,7 @@ int launch_fft_fast_r1(ta_ctx* ctx, std::vector<int>* grids) {
             a.series = s.series + (size_t)rg.a0 * ctx->D * ctx->Tld;
             a.by_particle = s.by_particle + (size_t)rg.a0 * ctx->Tld;
             a.natoms = (int)rg.n;
-            k1f_fft_acf<R1, NT, PROF><<<(int)std::min<int64_t>(grid, rg.n), nthr, smem, s.s_compute>>>(a);
+            k1f_fft_acf<R1, NT, PROF, VAR><<<(int)std::min<int64_t>(grid, rg.n), nthr, smem, s.s_compute>>>(a);
             CK(cudaGetLastError());
             ctx->launches++;
         }
@@ -580,20 +635,93 @@ int launch_fft_fast_r1(ta_ctx* ctx, std::vector<int>* grids) {
     return TA_OK;
 }
 
+template <int R>
+int launch_fft_r8_r(ta_ctx* ctx, std::vector<int>* grids) {
+    // TA_B200_K1E_ONE_CTA=1 (experiments): pad the shared memory request so that only one CTA fits on an SM
+    const int smem = env_int("TA_B200_K1E_ONE_CTA", 0) ? std::max(k1e_smem_bytes(R), 120 * 1024) : k1e_smem_bytes(R);
+    const int nthr = k1e_threads(R);
+    grids->assign(ctx->sh.size(), 0);
+    for (size_t i = 0; i < ctx->sh.size(); ++i) {
+        Shard& s = ctx->sh[i];
+        if (s.natoms == 0) continue;
+        CK(cudaSetDevice(s.dev));
+        if (smem > s.max_smem) return fail(ctx, TA_ERR_UNSUPPORTED, "radix-8 FFT kernel needs more shared memory than the device has");
+        CK(cudaFuncSetAttribute(k1e_fft_acf<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1e_fft_acf<R>, nthr, (size_t)smem));
+        if (occ < 1) return fail(ctx, TA_ERR_UNSUPPORTED, "radix-8 FFT kernel does not fit on an SM");
+        int grid = (int)std::min<int64_t>(s.natoms, (int64_t)s.num_sms * occ);
+        (*grids)[i] = grid;
+        int rc = ensure_partial(ctx, s, (size_t)grid);
+        if (rc) return rc;
+        K1EArgs a;
+        a.partial = s.partial;
+        a.omega = (const cd*)s.e_omega; a.tw2 = (const cd*)s.e_tw2; a.tw3 = (const cd*)s.e_tw3;
+        a.map = s.e_map; a.wbase = (const cd*)s.e_wbase;
+        a.D = ctx->D; a.T = (int)ctx->T; a.nh = (int)((ctx->T + 1) / 2); a.Tld = ctx->Tld;
+        a.sm_slots = s.e_slots;
+        a.stagger = occ >= 2 ? env_int("TA_B200_K1E_STAGGER", 0) : 0;
+        CK(cudaEventRecord(s.ev_ka, s.s_compute));
+        for (const LaunchRange& rg : take_launch_ranges(s)) {
+            if (rg.ready) CK(cudaStreamWaitEvent(s.s_compute, rg.ready, 0));
+            a.series = s.series + (size_t)rg.a0 * ctx->D * ctx->Tld;
+            a.by_particle = s.by_particle + (size_t)rg.a0 * ctx->Tld;
+            a.natoms = (int)rg.n;
+            if (a.stagger > 0) CK(cudaMemsetAsync(s.e_slots, 0, 1024 * sizeof(unsigned), s.s_compute));
+            k1e_fft_acf<R><<<(int)std::min<int64_t>(grid, rg.n), nthr, smem, s.s_compute>>>(a);
+            CK(cudaGetLastError());
+            ctx->launches++;
+        }
+        CK(cudaEventRecord(s.ev_kb, s.s_compute));
+        s.kernel_timed = true;
+        ctx->k1_threads = nthr; ctx->k1_smem = smem; ctx->k1_grid = grid;
+    }
+    return TA_OK;
+}
+
+int launch_fft_r8(ta_ctx* ctx, std::vector<int>* grids) {
+    switch (ctx->fast_r8) {
+        case 4: return launch_fft_r8_r<4>(ctx, grids);
+        case 5: return launch_fft_r8_r<5>(ctx, grids);
+        case 6: return launch_fft_r8_r<6>(ctx, grids);
+        case 8: return launch_fft_r8_r<8>(ctx, grids);
+        case 10: return launch_fft_r8_r<10>(ctx, grids);
+        case 12: return launch_fft_r8_r<12>(ctx, grids);
+    }
+    return fail(ctx, TA_ERR_UNSUPPORTED, "no radix-8 FFT instantiation for R=" + std::to_string(ctx->fast_r8));
+}
+
+// k1_fast.cuh VAR bits served per R1: 0 and 4 (bulk series prefetch) everywhere, the other experiments at R1 = 20.
+// Default: prefetch on (measured 25.4 -> 24.2 ms at 100k x 10k); TA_B200_K1F_VAR overrides.
+template <int R1>
+int launch_fft_fast_var(ta_ctx* ctx, std::vector<int>* grids) {
+    const int var = env_int("TA_B200_K1F_VAR", K1F_VAR_PREFETCH);
+    if (var == 0) return launch_fft_fast_r1<R1, k1f_threads(R1), false, 0>(ctx, grids);
+    if (var == 4) return launch_fft_fast_r1<R1, k1f_threads(R1), false, 4>(ctx, grids);
+    if constexpr (R1 == 20) {
+        if (var == 1) return launch_fft_fast_r1<20, k1f_threads(20), false, 1>(ctx, grids);
+        if (var == 2) return launch_fft_fast_r1<20, k1f_threads(20), false, 2>(ctx, grids);
+        if (var == 3) return launch_fft_fast_r1<20, k1f_threads(20), false, 3>(ctx, grids);
+        if (var == 5) return launch_fft_fast_r1<20, k1f_threads(20), false, 5>(ctx, grids);
+    }
+    return fail(ctx, TA_ERR_UNSUPPORTED, "no instantiation of the three-pass FFT kernel for TA_B200_K1F_VAR=" + std::to_string(var));
+}
+
 int launch_fft_fast(ta_ctx* ctx, std::vector<int>* grids) {
+    if (ctx->fast_r8 > 0) return launch_fft_r8(ctx, grids);
     switch (ctx->fast_r1) {
-        case 4: return launch_fft_fast_r1<4, k1f_threads(4)>(ctx, grids);
-        case 6: return launch_fft_fast_r1<6, k1f_threads(6)>(ctx, grids);
-        case 8: return launch_fft_fast_r1<8, k1f_threads(8)>(ctx, grids);
-        case 10: return launch_fft_fast_r1<10, k1f_threads(10)>(ctx, grids);
-        case 12: return launch_fft_fast_r1<12, k1f_threads(12)>(ctx, grids);
-        case 16: return launch_fft_fast_r1<16, k1f_threads(16)>(ctx, grids);
+        case 4: return launch_fft_fast_var<4>(ctx, grids);
+        case 6: return launch_fft_fast_var<6>(ctx, grids);
+        case 8: return launch_fft_fast_var<8>(ctx, grids);
+        case 10: return launch_fft_fast_var<10>(ctx, grids);
+        case 12: return launch_fft_fast_var<12>(ctx, grids);
+        case 16: return launch_fft_fast_var<16>(ctx, grids);
         case 20: {
             if (env_int("TA_B200_K1F_PROFILE", 0)) return launch_fft_fast_r1<20, k1f_threads(20), true>(ctx, grids);
             const int nt = env_int("TA_B200_K1F_NT", k1f_threads(20));   // experiments: two CTAs per SM
             if (nt == 192) return launch_fft_fast_r1<20, 192>(ctx, grids);
             if (nt == 160) return launch_fft_fast_r1<20, 160>(ctx, grids);
-            return launch_fft_fast_r1<20, k1f_threads(20)>(ctx, grids);
+            return launch_fft_fast_var<20>(ctx, grids);
         }
     }
     return fail(ctx, TA_ERR_UNSUPPORTED, "no fast FFT instantiation for R1=" + std::to_string(ctx->fast_r1));
@@ -1004,7 +1132,7 @@ int ta_vacf_fft(ta_ctx* ctx, double* ts_out) {
     if (!ts_out) return fail(ctx, TA_ERR_INVALID, "ts_out is null");
     if ((rc = ensure_fft_plan(ctx))) return rc;
     std::vector<int> grids;
-    if (ctx->fast_r1 > 0) rc = launch_fft_fast(ctx, &grids);
+    if (ctx->fast_r1 > 0 || ctx->fast_r8 > 0) rc = launch_fft_fast(ctx, &grids);
     else rc = (ctx->precision == TA_PRECISION_FP64) ? launch_fft<double>(ctx, &grids) : launch_fft<float>(ctx, &grids);
     if (rc) return rc;
     return finish_timeseries(ctx, grids, ts_out);
@@ -1048,7 +1176,7 @@ int ta_helfand_fft(ta_ctx* ctx, const double* volumes, double boltzmann, double 
     const double denom = 2 * boltzmann * (vsum / (double)ctx->T) * temp_avg;   // viscosity.py:205, :229-231
     if ((rc = ensure_fft_plan(ctx))) return rc;
     std::vector<int> grids;
-    rc = (ctx->fast_r1 > 0) ? launch_fft_fast(ctx, &grids) : launch_fft<double>(ctx, &grids);   // by_particle = sum_d acf_d
+    rc = (ctx->fast_r1 > 0 || ctx->fast_r8 > 0) ? launch_fft_fast(ctx, &grids) : launch_fft<double>(ctx, &grids);   // by_particle = sum_d acf_d
     if (rc) return rc;
     const size_t smem = ((size_t)ctx->T + 1) * sizeof(double);
     for (size_t i = 0; i < ctx->sh.size(); ++i) {
