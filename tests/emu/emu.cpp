@@ -90,6 +90,7 @@ static int run_k1fast(const double* series, int T, int D, int Tld, int natoms, i
     a.series = series; a.by_particle = by_particle; a.partial = partial;
     a.omega = reinterpret_cast<const cd*>(p.omega.data());
     a.tw2 = reinterpret_cast<const cd*>(p.tw2.data());
+    a.tw8 = reinterpret_cast<const cd*>(p.tw8.data());
     a.map = p.map.data();
     a.wbase = reinterpret_cast<const cd*>(p.wbase.data());
     a.inv = p.inv.data();
@@ -151,8 +152,11 @@ int emu_k1fast_var(const double* series, int T, int D, int Tld, int natoms, int 
         case 2: return run_k1fast<20, 2>(series, T, D, Tld, natoms, nblk, by_particle, partial);
         case 4: return run_k1fast<20, 4>(series, T, D, Tld, natoms, nblk, by_particle, partial);
         case 6: return run_k1fast<20, 6>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 8: return run_k1fast<20, 8>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 12: return run_k1fast<20, 12>(series, T, D, Tld, natoms, nblk, by_particle, partial);
     }
     if (R1 == 10) switch (var) {
+        case 12: return run_k1fast<10, 12>(series, T, D, Tld, natoms, nblk, by_particle, partial);
         case 2: return run_k1fast<10, 2>(series, T, D, Tld, natoms, nblk, by_particle, partial);
         case 4: return run_k1fast<10, 4>(series, T, D, Tld, natoms, nblk, by_particle, partial);
         case 6: return run_k1fast<10, 6>(series, T, D, Tld, natoms, nblk, by_particle, partial);

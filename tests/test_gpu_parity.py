@@ -299,7 +299,7 @@ def test_fft_default_kernel_choice(T, want):
     assert_close_normwise(v.results.timeseries, ref_ts, TOL64, f"T={T}")
 
 
-@pytest.mark.parametrize("var", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("var", [0, 1, 2, 3, 4, 5, 8, 12])
 def test_fft_three_pass_kernel_variants(var, monkeypatch):
     """k1_fast.cuh VAR bits at R1 = 20 (token-ordered loads, staged bulk output, bulk series prefetch = the default):
     same results whichever way the data moves.  N > 148 makes CTAs take several particles."""

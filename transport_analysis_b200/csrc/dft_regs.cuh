@@ -208,6 +208,58 @@ struct DftComposite {
     }
 };
 
+// ---------------------------------------------------------------------------
+// Radix-16 butterfly with a power sequence of one run-time twiddle on its inputs,
+//   y[k] = sum_q u[q] om^q exp(DIR 2 pi i q k / 16),
+// as four layers of radix-2 steps a +- t b in which the twiddle rides on the multiply of a fused multiply-add
+// (6 FMAs per step: p = a + t b, m = 2 a - p; 192 instructions instead of 60 for the multiplications by om^q plus 160
+// for the plain DFT).  Splitting the INPUT index by its top bit, q = q' + (M/2) b,
+//   y[2k']   = sum_q' (u[q'] + beta^(M/2) u[q'+M/2]) beta^q' w_(M/2)^(q'k')
+//   y[2k'+1] = sum_q' (u[q'] - beta^(M/2) u[q'+M/2]) (beta w_M)^q' w_(M/2)^(q'k')
+// every step of a layer uses beta^(M/2) = om^(M/2) w_16^(E M/2) with beta = om w_16^E, so the 32 steps draw on only eight
+// values: T = { om^8, om^4, om^2, om^2 w_8, om, om w_16, om w_16^2, om w_16^3 } (forward w = exp(-2 pi i / .)), each possibly
+// turned by a power of i, which costs nothing.  CONJ uses conj(T): the table of the inverse transform (DIR = +1).
+// T is read with stride TS at the point of use, so that no more than one or two twiddles are live at a time.
+// ---------------------------------------------------------------------------
+template <int ROT, bool CONJ, int DIR>
+TA_HD void bfly_tw(cd& a, cd& b, const cd tw) {
+    const double tx = tw.x, ty = CONJ ? -tw.y : tw.y;
+    constexpr int rr = ((ROT % 4) + 4) % 4;          // t = (tx + i ty) (DIR i)^rr
+    const double ux = rr == 0 ? tx : rr == 2 ? -tx : ((rr == 1) == (DIR > 0) ? -ty : ty);
+    const double uy = rr == 0 ? ty : rr == 2 ? -ty : ((rr == 1) == (DIR > 0) ? tx : -tx);
+    double px = fma(ux, b.x, a.x), py = fma(ux, b.y, a.y);
+    px = fma(-uy, b.y, px);
+    py = fma(uy, b.x, py);
+    b = cmake<double>(fma(2.0, a.x, -px), fma(2.0, a.y, -py));
+    a = cmake<double>(px, py);
+}
+
+template <int M, int E, int DIR, bool CONJ, int TS>
+struct TwDit {
+    static TA_HD void run(cd* u, const cd* T) {
+        constexpr int h = M / 2;
+        constexpr int ti = M == 16 ? 0 : M == 8 ? 1 : M == 4 ? (2 + (E & 1)) : (4 + (E & 3));
+        constexpr int rot = M == 16 ? 0 : M == 8 ? E : M == 4 ? (E >> 1) : (E >> 2);
+        cd a[h], b[h];
+        const cd t = T[ti * TS];
+        static_for<0, h>([&](auto iq) {
+            constexpr int q = decltype(iq)::value;
+            a[q] = u[q];
+            b[q] = u[q + h];
+            bfly_tw<rot, CONJ, DIR>(a[q], b[q], t);
+        });
+        if constexpr (h > 1) {
+            TwDit<h, E, DIR, CONJ, TS>::run(a, T);
+            TwDit<h, E + 16 / M, DIR, CONJ, TS>::run(b, T);
+        }
+        static_for<0, h>([&](auto ik) {
+            constexpr int k = decltype(ik)::value;
+            u[2 * k] = a[k];
+            u[2 * k + 1] = b[k];
+        });
+    }
+};
+
 template <int DIR> struct Dft<6, DIR> : DftComposite<2, 3, DIR> {};
 template <int DIR> struct Dft<8, DIR> : DftComposite<2, 4, DIR> {};
 template <int DIR> struct Dft<10, DIR> : DftComposite<2, 5, DIR> {};

@@ -45,6 +45,7 @@ struct K1FArgs {
     double* partial;             // [grid][Tld]
     const cd* omega;             // [256]      w_{2H}^j
     const cd* tw2;               // [15][16]   w_256^{j k}, k = 1..15
+    const cd* tw8;               // [8][16]    TwDit table of om = w_256^j (K1F_VAR_DEFTW)
     const uint32_t* map;         // [2][16 R1] per residue: bits 0-15 P3 butterfly of a thread, 16-23 its P2 block, 30/31 flags
     const cd* wbase;             // [2][16 R1] w_L^{2 G0 + r} of that butterfly
     const double* inv;           // [Tld]      1 / (L (T - k)), 0 beyond T
@@ -111,7 +112,11 @@ TA_HD void k1f_p1_twiddles(cd om, int r, cd* e, cd* g) {
 //      others and no warp waits for L2 / HBM
 constexpr int K1F_VAR_TURNS = 1;
 constexpr int K1F_VAR_STAGED = 2;
+//   8  deferred twiddles: the P2 -> P3 twiddles w_256^(j k) are not multiplied onto the P2 outputs (15 table loads and
+//      60 FP64 instructions per butterfly) but ride on the FMAs of the P3 butterfly (TwDit in dft_regs.cuh: 8 table loads,
+//      +32 instructions); the inverse P2' uses the same butterfly with the conjugate table
 constexpr int K1F_VAR_PREFETCH = 4;
+constexpr int K1F_VAR_DEFTW = 8;
 
 // Rank r (warps 4r .. 4r+3 of the first NW warps) may issue its loads once rank r-1 has issued its own.
 // Named barriers id0 + r; consecutive uses of one site are separated by a CTA barrier.
@@ -158,7 +163,8 @@ TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid,
     const double Ld = (double)(4 * H);
 
     for (int i = tid; i < 256; i += NT) s_om[i] = A.omega[i];
-    for (int i = tid; i < 240; i += NT) s_tw2[i] = A.tw2[i];
+    constexpr bool DEFTW = (VAR & K1F_VAR_DEFTW) != 0;
+    for (int i = tid; i < 240; i += NT) s_tw2[i] = DEFTW ? (i < 128 ? A.tw8[i] : cmake<double>(0.0, 0.0)) : A.tw2[i];
     if (PREF && tid == 0) Ctx::mbar_init(mbar);
     Ctx::sync();
 
@@ -260,8 +266,10 @@ TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid,
                     if (TURNS) k1f_turn_pass<Ctx, NW>(warp, 4);
                     K1F_TICK(3, x[15].y + x[0].x);
                     Dft<16, -1>::run(x);
+                    if (!DEFTW) {
 #pragma unroll
-                    for (int k = 1; k < 16; ++k) x[k] = cmul(x[k], s_tw2[(k - 1) * 16 + j2]);
+                        for (int k = 1; k < 16; ++k) x[k] = cmul(x[k], s_tw2[(k - 1) * 16 + j2]);
+                    }
                     K1F_TICK(4, x[15].y + x[1].x);
 #pragma unroll
                     for (int k = 0; k < 16; ++k) buf[p2base + 17 * k] = x[k];
@@ -281,7 +289,8 @@ TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid,
 #pragma unroll
                     for (int q = 0; q < 16; ++q) v[q] = buf[p3base + q];
                     K1F_TICK(6, v[15].y + v[0].x);
-                    Dft<16, -1>::run(v);
+                    if (DEFTW) TwDit<16, 0, -1, false, 16>::run(v, s_tw2 + (int)(mp & 15u));   // om = w_256^k2
+                    else Dft<16, -1>::run(v);
                     static_for<0, 8>([&](auto im) {
                         constexpr int m = decltype(im)::value;
                         cd snd = v[15 - m], rec;
@@ -344,10 +353,16 @@ TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid,
                 const int blk2 = (int)((A.map[r * NV + vt] >> 16) & 0xffu);
                 const int p2base = blk2 * 272 + j2;
                 cd x[16];
-                x[0] = buf[p2base];
+                if (DEFTW) {
 #pragma unroll
-                for (int k = 1; k < 16; ++k) x[k] = cmulc(buf[p2base + 17 * k], s_tw2[(k - 1) * 16 + j2]);
-                Dft<16, +1>::run(x);
+                    for (int k = 0; k < 16; ++k) x[k] = buf[p2base + 17 * k];
+                    TwDit<16, 0, +1, true, 16>::run(x, s_tw2 + j2);                          // om = conj(w_256^j2)
+                } else {
+                    x[0] = buf[p2base];
+#pragma unroll
+                    for (int k = 1; k < 16; ++k) x[k] = cmulc(buf[p2base + 17 * k], s_tw2[(k - 1) * 16 + j2]);
+                    Dft<16, +1>::run(x);
+                }
                 K1F_TICK(11, x[15].y + x[0].x);
 #pragma unroll
                 for (int q = 0; q < 16; ++q) buf[p2base + 17 * q] = x[q];
@@ -469,6 +484,7 @@ struct K1FastPlan {
     int R1 = 0, H = 0, L = 0, NT = 0, nh = 0;
     std::vector<double> omega;    // 256 x (re, im)
     std::vector<double> tw2;      // 240 x (re, im)
+    std::vector<double> tw8;      // 128 x (re, im)
     std::vector<uint32_t> map;    // 2 x NT
     std::vector<double> wbase;    // 2 x NT x (re, im)
     std::vector<double> inv;      // Tld
@@ -504,6 +520,11 @@ inline int k1f_build_plan(int64_t T, int64_t Tld, int R1, K1FastPlan* p) {
     for (int k = 1; k < 16; ++k)
         for (int j = 0; j < 16; ++j)
             ta_twiddle((int64_t)j * k, 256, &p->tw2[2 * ((k - 1) * 16 + j)], &p->tw2[2 * ((k - 1) * 16 + j) + 1]);
+    p->tw8.resize(2 * 128);
+    for (int j = 0; j < 16; ++j) {
+        const int64_t ex[8] = {8 * j, 4 * j, 2 * j, 2 * j + 32, j, j + 16, j + 32, j + 48};   // exponents of w_256
+        for (int v = 0; v < 8; ++v) ta_twiddle(ex[v], 256, &p->tw8[2 * (v * 16 + j)], &p->tw8[2 * (v * 16 + j) + 1]);
+    }
     const int NT = p->NT;
     p->map.assign(2 * (size_t)NT, 0);
     p->wbase.assign(4 * (size_t)NT, 0.0);

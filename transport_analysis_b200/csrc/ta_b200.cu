@@ -118,6 +118,7 @@ struct Shard {
     // fast-path FFT tables (k1_fast.cuh)
     void* f_omega = nullptr;
     void* f_tw2 = nullptr;
+    void* f_tw8 = nullptr;
     uint32_t* f_map = nullptr;
     void* f_wbase = nullptr;
     double* f_inv = nullptr;
@@ -212,6 +213,7 @@ void free_problem(ta_ctx* c) {
         cudaFree(s.own0); s.own0 = nullptr;
         cudaFree(s.f_omega); s.f_omega = nullptr;
         cudaFree(s.f_tw2); s.f_tw2 = nullptr;
+        cudaFree(s.f_tw8); s.f_tw8 = nullptr;
         cudaFree(s.f_map); s.f_map = nullptr;
         cudaFree(s.f_wbase); s.f_wbase = nullptr;
         cudaFree(s.f_inv); s.f_inv = nullptr;
@@ -425,13 +427,14 @@ int upload_fft_tables(ta_ctx* ctx, const std::vector<uint32_t>& own0) {
 int upload_fast_tables(ta_ctx* ctx, const K1FastPlan& p) {
     for (auto& s : ctx->sh) {
         CK(cudaSetDevice(s.dev));
-        cudaFree(s.f_omega); cudaFree(s.f_tw2); cudaFree(s.f_map); cudaFree(s.f_wbase); cudaFree(s.f_inv);
-        s.f_omega = s.f_tw2 = s.f_wbase = nullptr; s.f_map = nullptr; s.f_inv = nullptr;
+        cudaFree(s.f_omega); cudaFree(s.f_tw2); cudaFree(s.f_tw8); cudaFree(s.f_map); cudaFree(s.f_wbase); cudaFree(s.f_inv);
+        s.f_omega = s.f_tw2 = s.f_tw8 = s.f_wbase = nullptr; s.f_map = nullptr; s.f_inv = nullptr;
 #define TA_UP(dst, vec)                                                                         \
         CK(cudaMalloc((void**)&dst, vec.size() * sizeof(vec[0])));                              \
         CK(cudaMemcpy(dst, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice));
         TA_UP(s.f_omega, p.omega);
         TA_UP(s.f_tw2, p.tw2);
+        TA_UP(s.f_tw8, p.tw8);
         TA_UP(s.f_map, p.map);
         TA_UP(s.f_wbase, p.wbase);
         TA_UP(s.f_inv, p.inv);
@@ -591,7 +594,7 @@ int launch_fft_fast_r1(ta_ctx* ctx, std::vector<int>* grids) {
         if (rc) return rc;
         K1FArgs a;
         a.partial = s.partial;
-        a.omega = (const cd*)s.f_omega; a.tw2 = (const cd*)s.f_tw2; a.map = s.f_map;
+        a.omega = (const cd*)s.f_omega; a.tw2 = (const cd*)s.f_tw2; a.tw8 = (const cd*)s.f_tw8; a.map = s.f_map;
         a.wbase = (const cd*)s.f_wbase; a.inv = s.f_inv;
         a.D = ctx->D; a.T = (int)ctx->T; a.nh = (int)((ctx->T + 1) / 2); a.Tld = ctx->Tld;
         a.prefetch = env_int("TA_B200_K1F_PREFETCH", 0);
@@ -698,11 +701,13 @@ int launch_fft_fast_var(ta_ctx* ctx, std::vector<int>* grids) {
     const int var = env_int("TA_B200_K1F_VAR", K1F_VAR_PREFETCH);
     if (var == 0) return launch_fft_fast_r1<R1, k1f_threads(R1), false, 0>(ctx, grids);
     if (var == 4) return launch_fft_fast_r1<R1, k1f_threads(R1), false, 4>(ctx, grids);
+    if (var == 12) return launch_fft_fast_r1<R1, k1f_threads(R1), false, 12>(ctx, grids);
     if constexpr (R1 == 20) {
         if (var == 1) return launch_fft_fast_r1<20, k1f_threads(20), false, 1>(ctx, grids);
         if (var == 2) return launch_fft_fast_r1<20, k1f_threads(20), false, 2>(ctx, grids);
         if (var == 3) return launch_fft_fast_r1<20, k1f_threads(20), false, 3>(ctx, grids);
         if (var == 5) return launch_fft_fast_r1<20, k1f_threads(20), false, 5>(ctx, grids);
+        if (var == 8) return launch_fft_fast_r1<20, k1f_threads(20), false, 8>(ctx, grids);
     }
     return fail(ctx, TA_ERR_UNSUPPORTED, "no instantiation of the three-pass FFT kernel for TA_B200_K1F_VAR=" + std::to_string(var));
 }
