@@ -298,6 +298,20 @@ k1f_fft_acf(const K1FArgs args) {
     k1f_body<R1, NT, DevCtx, PROF, VAR>(args, smem_raw, (int)threadIdx.x, (int)blockIdx.x, (int)gridDim.x);
 }
 
+// The same kernel with the register cap stated outright instead of derived from launch bounds.  With ten warps per SM
+// (three on two of the sub-partitions, 16,384 registers each) 170 registers per thread is the ceiling either way, but ptxas
+// schedules differently under the two attributes: __launch_bounds__(320, 1) gives 168 registers and 16-32 B of spills,
+// __maxnreg__(184) 166 registers and none -- 24.2 -> 23.5 ms at 100k x 10k (caps 152 / 160 / 168 / 176 / 184: 24.21 / 24.08 /
+// 23.66 / 23.52 / 23.46 ms; 200 does not fit).  Used for NT = 320 (R1 = 20) only: at NT = 160 the same cap yields 174
+// registers, which would leave one CTA per SM instead of two.
+constexpr int K1F_MAXREG = 184;
+template <int R1, int NT, int VAR, int MAXREG>
+__global__ void __maxnreg__(MAXREG)
+k1f_fft_acf_mr(const K1FArgs args) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    k1f_body<R1, NT, DevCtx, false, VAR>(args, smem_raw, (int)threadIdx.x, (int)blockIdx.x, (int)gridDim.x);
+}
+
 // ---------------------------------------------------------------------------
 // K1 radix-8 path (k1_r8.cuh): H = 512 R in four passes, 64 R threads, one CTA per SM.
 // ---------------------------------------------------------------------------

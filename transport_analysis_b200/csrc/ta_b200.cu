@@ -576,7 +576,7 @@ int env_int(const char* name, int dflt) {
 }
 
 template <int R1, int NT, bool PROF = false, int VAR = 0>
-int launch_fft_fast_r1(ta_ctx* ctx, std::vector<int>* grids) {
+int launch_fft_fast_r1(ta_ctx* ctx, std::vector<int>* grids, void (*kern)(const K1FArgs) = k1f_fft_acf<R1, NT, PROF, VAR>) {
     const int smem = k1f_smem_bytes(R1, VAR);
     const int nthr = NT;
     grids->assign(ctx->sh.size(), 0);
@@ -584,9 +584,9 @@ int launch_fft_fast_r1(ta_ctx* ctx, std::vector<int>* grids) {
         Shard& s = ctx->sh[i];
         if (s.natoms == 0) continue;
         CK(cudaSetDevice(s.dev));
-        CK(cudaFuncSetAttribute(k1f_fft_acf<R1, NT, PROF, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1f_fft_acf<R1, NT, PROF, VAR>, nthr, (size_t)smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nthr, (size_t)smem));
         if (occ < 1) return fail(ctx, TA_ERR_UNSUPPORTED, "fast FFT kernel does not fit on an SM");
         int grid = (int)std::min<int64_t>(s.natoms, (int64_t)s.num_sms * occ);
         (*grids)[i] = grid;
@@ -611,7 +611,7 @@ int launch_fft_fast_r1(ta_ctx* ctx, std::vector<int>* grids) {
             a.series = s.series + (size_t)rg.a0 * ctx->D * ctx->Tld;
             a.by_particle = s.by_particle + (size_t)rg.a0 * ctx->Tld;
             a.natoms = (int)rg.n;
-            k1f_fft_acf<R1, NT, PROF, VAR><<<(int)std::min<int64_t>(grid, rg.n), nthr, smem, s.s_compute>>>(a);
+            kern<<<(int)std::min<int64_t>(grid, rg.n), nthr, smem, s.s_compute>>>(a);
             CK(cudaGetLastError());
             ctx->launches++;
         }
@@ -699,9 +699,16 @@ int launch_fft_r8(ta_ctx* ctx, std::vector<int>* grids) {
 template <int R1>
 int launch_fft_fast_var(ta_ctx* ctx, std::vector<int>* grids) {
     const int var = env_int("TA_B200_K1F_VAR", K1F_VAR_PREFETCH);
-    if (var == 0) return launch_fft_fast_r1<R1, k1f_threads(R1), false, 0>(ctx, grids);
-    if (var == 4) return launch_fft_fast_r1<R1, k1f_threads(R1), false, 4>(ctx, grids);
-    if (var == 12) return launch_fft_fast_r1<R1, k1f_threads(R1), false, 12>(ctx, grids);
+    constexpr int NT = k1f_threads(R1);
+    if (var == 0) return launch_fft_fast_r1<R1, NT, false, 0>(ctx, grids);
+    if (var == 4) {
+        // ten warps per SM: register cap stated with __maxnreg__ (kernels.cuh); TA_B200_K1F_MAXREG=0 keeps the launch bounds
+        if constexpr (NT == 320)
+            if (env_int("TA_B200_K1F_MAXREG", K1F_MAXREG) == K1F_MAXREG)
+                return launch_fft_fast_r1<R1, NT, false, 4>(ctx, grids, k1f_fft_acf_mr<R1, NT, 4, K1F_MAXREG>);
+        return launch_fft_fast_r1<R1, NT, false, 4>(ctx, grids);
+    }
+    if (var == 12) return launch_fft_fast_r1<R1, NT, false, 12>(ctx, grids);
     if constexpr (R1 == 20) {
         if (var == 1) return launch_fft_fast_r1<20, k1f_threads(20), false, 1>(ctx, grids);
         if (var == 2) return launch_fft_fast_r1<20, k1f_threads(20), false, 2>(ctx, grids);
@@ -726,6 +733,9 @@ int launch_fft_fast(ta_ctx* ctx, std::vector<int>* grids) {
             const int nt = env_int("TA_B200_K1F_NT", k1f_threads(20));   // experiments: two CTAs per SM
             if (nt == 192) return launch_fft_fast_r1<20, 192>(ctx, grids);
             if (nt == 160) return launch_fft_fast_r1<20, 160>(ctx, grids);
+            const int mr = env_int("TA_B200_K1F_MAXREG", K1F_MAXREG);      // experiments: other explicit register caps
+            if (mr == 160) return launch_fft_fast_r1<20, 320, false, 4>(ctx, grids, k1f_fft_acf_mr<20, 320, 4, 160>);
+            if (mr == 168) return launch_fft_fast_r1<20, 320, false, 4>(ctx, grids, k1f_fft_acf_mr<20, 320, 4, 168>);
             return launch_fft_fast_var<20>(ctx, grids);
         }
     }
