@@ -154,6 +154,7 @@ int emu_k1fast_var(const double* series, int T, int D, int Tld, int natoms, int 
         case 6: return run_k1fast<20, 6>(series, T, D, Tld, natoms, nblk, by_particle, partial);
         case 8: return run_k1fast<20, 8>(series, T, D, Tld, natoms, nblk, by_particle, partial);
         case 12: return run_k1fast<20, 12>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 52: return run_k1fast<20, 52>(series, T, D, Tld, natoms, nblk, by_particle, partial);
     }
     if (R1 == 10) switch (var) {
         case 12: return run_k1fast<10, 12>(series, T, D, Tld, natoms, nblk, by_particle, partial);

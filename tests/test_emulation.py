@@ -199,10 +199,11 @@ def test_radix8_plan_thread_maps(emu, R):
 
 
 @pytest.mark.parametrize("T,R1,var", [(10000, 20, 1), (10000, 20, 2), (9999, 20, 4), (10000, 20, 6), (5001, 10, 2),
-                                      (5000, 10, 4), (4999, 10, 6), (10000, 20, 8), (9999, 20, 12), (5001, 10, 12)])
+                                      (5000, 10, 4), (4999, 10, 6), (10000, 20, 8), (9999, 20, 12), (5001, 10, 12),
+                                      (9999, 20, 52)])
 def test_fast_fft_kernel_variants(emu, T, R1, var):
     """k1_fast.cuh VAR bits: token-ordered loads (1), staged bulk output (2), bulk series prefetch (4), deferred
-    P2 -> P3 twiddles (8)."""
+    P2 -> P3 twiddles (8), output in chunks of 10 (16), computed 1 / (L (T - k)) (32)."""
     N, D, nblk = 3, 3, 2
     x = np.random.default_rng(T + var).standard_normal((T, N, D))
     Tld = (T + 15) // 16 * 16

@@ -116,7 +116,11 @@ constexpr int K1F_VAR_STAGED = 2;
 //      60 FP64 instructions per butterfly) but ride on the FMAs of the P3 butterfly (TwDit in dft_regs.cuh: 8 table loads,
 //      +32 instructions); the inverse P2' uses the same butterfly with the conjugate table
 constexpr int K1F_VAR_PREFETCH = 4;
+//  16  output phase in chunks of 10 elements per thread instead of 5 (two L2 round trips instead of four)
+//  32  1 / (L (T - k)) computed (hardware reciprocal seed + two Newton steps) instead of loaded from the table
 constexpr int K1F_VAR_DEFTW = 8;
+constexpr int K1F_VAR_OUT10 = 16;
+constexpr int K1F_VAR_RCPINV = 32;
 
 // Rank r (warps 4r .. 4r+3 of the first NW warps) may issue its loads once rank r-1 has issued its own.
 // Named barriers id0 + r; consecutive uses of one site are separated by a CTA barrier.
@@ -427,7 +431,8 @@ TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid,
 #pragma unroll
                     for (int q = 0; q < R1; ++q) own[272 * q] = x[q];
                     Ctx::compiler_fence();
-                    constexpr int QB = (R1 % 5 == 0) ? 5 : 4;
+                    constexpr bool OUT10 = (VAR & K1F_VAR_OUT10) != 0, RCPINV = (VAR & K1F_VAR_RCPINV) != 0;
+                    constexpr int QB = OUT10 ? ((R1 % 10 == 0) ? 10 : 8) : ((R1 % 5 == 0) ? 5 : 4);
                     static_for<0, (R1 + QB - 1) / QB>([&](auto ic) {
                         constexpr int q0 = decltype(ic)::value * QB;
                         constexpr int nq = (R1 - q0) < QB ? (R1 - q0) : QB;
@@ -436,12 +441,18 @@ TA_HD void k1f_body(const K1FArgs& A, unsigned char* smem_raw, int tid, int bid,
                         for (int i = 0; i < nq; ++i) {
                             const int n = j + 256 * (q0 + i);
                             const int nc = n < nh ? n : nh - 1;      // clamped: the loads stay branch-free
-                            a[i] = Ctx::ld_stream(row + nc); sc[i] = inv2[nc]; ps[i] = Ctx::ld_stream(part + nc);
+                            a[i] = Ctx::ld_stream(row + nc); ps[i] = Ctx::ld_stream(part + nc);
+                            if (!RCPINV) sc[i] = inv2[nc];
                         }
 #pragma unroll
                         for (int i = 0; i < nq; ++i) {
                             const int n = j + 256 * (q0 + i);
                             if (n < nh) {
+                                if (RCPINV) {
+                                    const int k = 2 * n;
+                                    sc[i].x = Ctx::rcp(Ld * (double)(A.T - k));
+                                    sc[i].y = k + 1 < A.T ? Ctx::rcp(Ld * (double)(A.T - k - 1)) : 0.0;
+                                }
                                 const cd v1 = own[272 * (q0 + i)];
                                 const cd o = cmake<double>((a[i].x + v1.x) * sc[i].x, (a[i].y + v1.y) * sc[i].y);
                                 row[n] = o;
