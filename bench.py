@@ -32,6 +32,10 @@ import time
 
 import numpy as np
 
+# stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ..." when NCCL_DEBUG is set in the environment)
+# goes to stderr instead of stdout
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -232,6 +236,37 @@ def workload_config(workload, A, T, gpus):
             if A * T * 24 > 2 * 126e6 else "L2 flushed between steps"}
 
 
+def bind_near_gpu(device_index):
+    """Pin this process (and the threads it starts later) to the CPUs of the GPU's NUMA node, before the host
+    trajectory is allocated: first touch then places the pages next to the PCIe root the copies leave from.
+    What `numactl --cpunodebind` would do for a one-process-per-GPU launch; returns a description for the JSON line."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:           # nvml prints an 8-digit PCI domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read())
+        if node < 0:
+            return {"node": None, "why": "single NUMA node"}
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"node": node, "why": "no allowed CPU on that node"}
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus)}
+    except Exception as e:  # no nvml / sysfs: run unbound
+        return {"node": None, "why": f"{type(e).__name__}: {e}"[:80]}
+
+
 # ---------------------------------------------------------------- B200 arm
 def run_b200(args, rank, world, local_rank):
     from transport_analysis_b200 import _lib
@@ -239,6 +274,7 @@ def run_b200(args, rank, world, local_rank):
     from transport_analysis_b200.velocityautocorr import VelocityAutocorr
     from transport_analysis_b200.viscosity import ViscosityHelfand
 
+    numa = bind_near_gpu(local_rank) if not args.no_numa_bind else {"node": None, "why": "--no-numa-bind"}
     dist = None
     if world > 1:
         import torch.distributed as dist  # plumbing only: rendezvous, barrier, max-over-ranks
@@ -372,7 +408,7 @@ def run_b200(args, rank, world, local_rank):
             "metric": "atom-frames/s", "value": value, "unit": "atom-frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(workload, A, T, world),
+            "config": dict(workload_config(workload, A, T, world), host_numa_binding=numa),
             "e2e": {"value": e2e_value, "unit": "atom-frames/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": {"fft": "VelocityAutocorr(ag, fft=True).run()", "windowed": "VelocityAutocorr(ag, fft=False).run()",
@@ -409,6 +445,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="fft", choices=["fft", "windowed", "helfand", "helfand_fft"])
     ap.add_argument("--atoms", type=int, default=0, help="atoms per GPU (default: BASELINE config)")
+    ap.add_argument("--no-numa-bind", action="store_true",
+                    help="do not pin the rank to the CPUs of its GPU's NUMA node before allocating the host trajectory")
     ap.add_argument("--frames", type=int, default=0)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
