@@ -32,9 +32,16 @@ import time
 
 import numpy as np
 
-# stdout carries exactly one JSON line: NCCL's own banner ("NCCL version ..." when NCCL_DEBUG is set in the environment)
-# goes to stderr instead of stdout
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly one JSON line.  Libraries write there too (NCCL prints "NCCL version ..." to stdout when
+# NCCL_DEBUG=VERSION is set in the environment, NCCL_DEBUG_FILE notwithstanding), so file descriptor 1 is pointed at stderr
+# for the whole run and the JSON line goes to the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: str):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (line + "\n").encode())
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -223,7 +230,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": value, "unit": "atom-frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "atom-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 def workload_config(workload, A, T, gpus):
@@ -418,7 +425,7 @@ def run_b200(args, rank, world, local_rank):
             "fft_plan": ctx.fft_plan_info() if workload == "fft" else None,
             "setup_s": setup_s,
         }
-        print(json.dumps(line))
+        emit(json.dumps(line))
     _lib.host_unregister(vel)
     if pos is not None:
         _lib.host_unregister(pos)
