@@ -35,11 +35,21 @@ import numpy as np
 # stdout carries exactly one JSON line.  Libraries write there too (NCCL prints "NCCL version ..." to stdout when
 # NCCL_DEBUG=VERSION is set in the environment, NCCL_DEBUG_FILE notwithstanding), so file descriptor 1 is pointed at stderr
 # for the whole run and the JSON line goes to the saved descriptor.
-_REAL_STDOUT = os.dup(1)
-os.dup2(2, 1)
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
 
 
 def emit(line: str):
+    if _REAL_STDOUT is None:
+        print(line, flush=True)
+        return
     sys.stdout.flush()
     os.write(_REAL_STDOUT, (line + "\n").encode())
 
@@ -456,6 +466,7 @@ def main():
                     help="do not pin the rank to the CPUs of its GPU's NUMA node before allocating the host trajectory")
     ap.add_argument("--frames", type=int, default=0)
     args = ap.parse_args()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -358,6 +358,83 @@ def test_properties_at_config_sizes():
     assert_allclose(v2.results.vacf_by_particle, 4.0 * bp[:, :256], rtol=1e-12, atol=1e-12 * np.abs(bp).max())
 
 
+def test_properties_at_config4_full_size():
+    """BASELINE config 4 at full size (100,000 particles x 10,000 frames, the bench workload): the oracle cannot run it, so
+    (a) sampled particles against the oracle, (b) lag 0 of sampled particles equals their mean square, (c) the timeseries
+    equals the mean over ALL per-particle rows (fetched range by range from the device), (d) a scaled sub-range gives the
+    scaled result, (e) a second run returns the same bits.  Needs ~25 GB of host memory and one GPU with 40 GB free."""
+    import bench
+
+    T, N = 10000, 100000
+    try:
+        vel = np.empty((T, N, 3), dtype=np.float32)
+    except MemoryError:
+        pytest.skip("not enough host memory for the full-size trajectory")
+    bench.fill_random_f32(vel, seed=99)
+    u = make_universe(None, vel)
+    v = VACF(u.atoms, fft=True).run()
+    assert v._ctx.fft_plan_info()["radices"] == [20, 16, 16]
+    ts, lazy = v.results.timeseries, v.results.vacf_by_particle       # 8 GB: stays on the device behind a lazy handle
+    assert lazy.shape == (T, N)
+    pick = [0, 1, 31337, 49999, 50000, 77777, 99998, 99999]
+    ref_bp, _ = oracle.vacf_fft(_f64(vel[:, pick]))
+    got = np.stack([lazy.particles(p, p + 1)[:, 0] for p in pick], axis=1)
+    assert_close_normwise(got, ref_bp, TOL64, "sampled particles vs oracle")
+    assert_allclose(got[0], (_f64(vel[:, pick]) ** 2).sum(axis=2).mean(axis=0), rtol=1e-12)
+    total = np.zeros(T)
+    for a in range(0, N, 5000):
+        total += lazy.particles(a, a + 5000).sum(axis=1)
+    assert_allclose(ts, total / N, rtol=1e-11, atol=1e-13 * np.abs(ts).max())
+    again = VACF(u.atoms, fft=True).run()
+    assert np.array_equal(again.results.timeseries, ts)
+    sub = vel[:, 1000:1512] * np.float32(2.0)
+    v2 = VACF(make_universe(None, sub).atoms, fft=True).run()
+    assert_allclose(v2.results.vacf_by_particle, 4.0 * lazy.particles(1000, 1512), rtol=1e-12, atol=1e-12 * np.abs(ref_bp).max())
+
+
+def test_properties_at_config2_and_config3_full_size():
+    """BASELINE config 2 (windowed VACF, 1,000 x 2,000) and config 3 (Helfand, 10,000 x 5,000) at full size: sampled
+    particles against the oracle, windowed == FFT route on all particles, Helfand row 0 == 0, timeseries == particle mean,
+    g -> 2 g gives 4 x the Helfand MSD, opt-in FFT route of the Helfand MSD within its stated 1e-7."""
+    import bench
+
+    # ---- config 2
+    T, N = 2000, 1000
+    vel = np.empty((T, N, 3), dtype=np.float32)
+    bench.fill_random_f32(vel, seed=7)
+    u = make_universe(None, vel)
+    w = VACF(u.atoms, fft=False).run()
+    f = VACF(u.atoms, fft=True).run()
+    assert_close_normwise(w.results.vacf_by_particle, f.results.vacf_by_particle, TOL64, "windowed vs FFT, all particles")
+    pick = [0, 499, 500, 999]
+    ref_bp, _ = oracle.vacf_windowed(_f64(vel[:, pick]))
+    assert_close_normwise(w.results.vacf_by_particle[:, pick], ref_bp, TOL64, "windowed vs oracle")
+    assert_allclose(w.results.timeseries, w.results.vacf_by_particle.mean(axis=1), rtol=1e-12,
+                    atol=1e-13 * np.abs(w.results.timeseries).max())
+    # ---- config 3
+    T, N = 5000, 10000
+    vel = np.empty((T, N, 3), dtype=np.float32)
+    pos = np.empty((T, N, 3), dtype=np.float32)
+    bench.fill_random_f32(vel, seed=8)
+    bench.fill_random_f32(pos, seed=9)
+    pos *= np.float32(10.0)
+    masses = np.random.default_rng(3).choice([1.008, 12.011, 15.999], N)
+    u = make_universe(pos, vel, masses=masses, dimensions=BOX)
+    h = VH(u.atoms).run()
+    bp, ts = np.asarray(h.results.visc_by_particle), h.results.timeseries
+    assert ts[0] == 0.0 and np.all(bp[0] == 0.0)
+    assert_allclose(ts, bp.mean(axis=1), rtol=1e-12)
+    pick = [0, 1, 5000, 9999]
+    vols = np.full(T, float(np.prod(np.float32(BOX[:3]).astype(np.float64))))
+    lags = [1, 2, 1250, 2500, 3750, 4998, 4999]
+    ref_bp, _ = oracle.helfand_msd(_f64(vel[:, pick]), _f64(pos[:, pick]), masses[pick], vols, 300.0, lags=lags)
+    assert_allclose(bp[lags][:, pick], ref_bp[lags], rtol=TOL64)
+    hf = VH(u.atoms, fft=True).run()
+    assert_allclose(hf.results.timeseries, ts, rtol=1e-7)
+    h2 = VH(make_universe(pos[:, :256], vel[:, :256] * np.float32(2.0), masses=masses[:256], dimensions=BOX).atoms).run()
+    assert_allclose(np.asarray(h2.results.visc_by_particle), 4.0 * bp[:, :256], rtol=1e-12)
+
+
 def test_multi_gpu_sharding_matches_single():
     n = _lib.device_count()
     if n < 2:
