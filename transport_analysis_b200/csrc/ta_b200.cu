@@ -731,6 +731,9 @@ int launch_fft_fast(ta_ctx* ctx, std::vector<int>* grids) {
         case 20: {
             if (env_int("TA_B200_K1F_PROFILE", 0)) return launch_fft_fast_r1<20, k1f_threads(20), true>(ctx, grids);
             const int nt = env_int("TA_B200_K1F_NT", k1f_threads(20));   // experiments: two CTAs per SM
+            // few fat warps: one (two) per sub-partition, 255 registers, several butterflies per thread and pass
+            if (nt == 128) return launch_fft_fast_r1<20, 128, false, 4>(ctx, grids, k1f_fft_acf_mr<20, 128, 4, 255>);
+            if (nt == 256) return launch_fft_fast_r1<20, 256, false, 4>(ctx, grids, k1f_fft_acf_mr<20, 256, 4, 255>);
             if (nt == 192) return launch_fft_fast_r1<20, 192>(ctx, grids);
             if (nt == 160) return launch_fft_fast_r1<20, 160>(ctx, grids);
             const int mr = env_int("TA_B200_K1F_MAXREG", K1F_MAXREG);      // experiments: other explicit register caps
