@@ -704,8 +704,16 @@ int launch_fft_fast_var(ta_ctx* ctx, std::vector<int>* grids) {
     if (var == 4) {
         // ten warps per SM: register cap stated with __maxnreg__ (kernels.cuh); TA_B200_K1F_MAXREG=0 keeps the launch bounds
         if constexpr (NT == 320)
-            if (env_int("TA_B200_K1F_MAXREG", K1F_MAXREG) == K1F_MAXREG)
-                return launch_fft_fast_r1<R1, NT, false, 4>(ctx, grids, k1f_fft_acf_mr<R1, NT, 4, K1F_MAXREG>);
+            if (env_int("TA_B200_K1F_MAXREG", K1F_MAXREG) == K1F_MAXREG) {
+                // the cap is above what fits (170); should a compiler settle higher than the 166 it uses today, the
+                // launch-bounds build of the same kernel takes over
+                int occ = 0;
+                cudaFuncSetAttribute(k1f_fft_acf_mr<R1, NT, 4, K1F_MAXREG>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1f_smem_bytes(R1, 4));
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1f_fft_acf_mr<R1, NT, 4, K1F_MAXREG>, NT,
+                                                                  (size_t)k1f_smem_bytes(R1, 4)) == cudaSuccess && occ >= 1)
+                    return launch_fft_fast_r1<R1, NT, false, 4>(ctx, grids, k1f_fft_acf_mr<R1, NT, 4, K1F_MAXREG>);
+                cudaGetLastError();
+            }
         return launch_fft_fast_r1<R1, NT, false, 4>(ctx, grids);
     }
     if (var == 12) return launch_fft_fast_r1<R1, NT, false, 12>(ctx, grids);
