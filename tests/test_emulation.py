@@ -39,7 +39,7 @@ def emu_win(lib, x, mode, nwarps=4, f32=0):
     return res
 
 
-@pytest.mark.parametrize("T", [1, 2, 3, 5, 10, 16, 17, 31, 33, 99, 100, 129, 250, 1000, 2047, 5001])
+@pytest.mark.parametrize("T", [1, 2, 3, 5, 10, 16, 17, 31, 33, 99, 100, 129, 250, 1000, 2047, 5001, 20001])
 def test_fft_phases_match_tidynamics_restatement(emu, T):
     rng = np.random.default_rng(T)
     for D in (1, 2, 3):

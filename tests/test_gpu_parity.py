@@ -317,6 +317,25 @@ def test_fft_three_pass_kernel_variants(var, monkeypatch):
     assert np.array_equal(again.results.vacf_by_particle, v.results.vacf_by_particle)
 
 
+@pytest.mark.parametrize("T,N,dim", [(19000, 3, "xyz"), (20001, 150, "xyz"), (30000, 2, "y"), (65536, 2, "xz")])
+def test_fft_route_beyond_shared_memory(T, N, dim):
+    """Trajectories whose FFT buffer does not fit in shared memory (T > ~19,000 in FP64) run the general kernel on a
+    per-CTA global work area: the FFT route never refuses a length.  Against the oracle; N > 148 reuses work areas."""
+    vel, _ = random_trajectory(T, N, seed=T % 97, rho=0.9)
+    u = make_universe(None, vel)
+    cols, _ = oracle.parse_dim_type(dim)
+    v = VACF(u.atoms, dim_type=dim, fft=True).run()
+    info = v._ctx.fft_plan_info()
+    assert info["H"] >= (T + 1) // 2 and info["smem_bytes"] < 100_000, info
+    n_or = min(N, 3)
+    ref_bp, _ = oracle.vacf_fft(_f64(vel)[:, :n_or, cols])
+    assert_close_normwise(v.results.vacf_by_particle[:, :n_or], ref_bp, TOL64, f"T={T} by particle")
+    assert_close_normwise(v.results.timeseries, v.results.vacf_by_particle.mean(axis=1), 1e-13, "timeseries = particle mean")
+    if N <= 3:
+        _, ref_ts = oracle.vacf_fft(_f64(vel)[:, :, cols])
+        assert_close_normwise(v.results.timeseries, ref_ts, TOL64, f"T={T} timeseries")
+
+
 def test_fft_fast_path_ramp_known_answer(monkeypatch):
     """The reference's step trajectory (v = t, 5001 frames) takes the fast path (R1 = 10)."""
     monkeypatch.setenv("TA_B200_K1_PATH", "r16")

@@ -70,19 +70,25 @@ struct K1Args {
     double* partial;             // [gridDim.x][Tld]
     int natoms, D;
     long long Tld;
+    unsigned char* scratch;      // SCRATCH: per-CTA work area in global memory (FFT buffer + pair accumulators)
+    long long scratch_stride;    // bytes per CTA
 };
 
 constexpr int K1_MAX_THREADS = 640;
 
-template <typename R>
+// SCRATCH = false: the H-point buffer and the pair accumulators live in shared memory (H up to ~9,600 in FP64).
+// SCRATCH = true : they live in a per-CTA global work area (served by L2), the twiddle tables stay in shared memory:
+//                  the same passes, slower, for any T -- the FFT route never has to refuse a trajectory for its length.
+template <typename R, bool SCRATCH = false>
 __global__ void __launch_bounds__(K1_MAX_THREADS)
 k1_fft_acf(const K1Args<R> args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int H = args.t.H;
-    cplx<R>* buf = reinterpret_cast<cplx<R>*>(smem_raw);
-    cplx<R>* tw_lo = buf + H;
+    unsigned char* work = SCRATCH ? args.scratch + (size_t)blockIdx.x * (size_t)args.scratch_stride : smem_raw;
+    cplx<R>* buf = reinterpret_cast<cplx<R>*>(work);
+    cplx<R>* tw_lo = SCRATCH ? reinterpret_cast<cplx<R>*>(smem_raw) : buf + H;
     cplx<R>* tw_hi = tw_lo + args.nlo;
-    R* sd = reinterpret_cast<R*>(tw_hi + args.nhi);
+    R* sd = SCRATCH ? reinterpret_cast<R*>(buf + H) : reinterpret_cast<R*>(tw_hi + args.nhi);
 
     const int tid = threadIdx.x, nthr = blockDim.x;
     FftTables<R> t = args.t;

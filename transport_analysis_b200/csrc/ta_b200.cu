@@ -520,9 +520,10 @@ template <typename R>
 int launch_fft(ta_ctx* ctx, std::vector<int>* grids) {
     const FftPlanHost& p = ctx->plan;
     const int nlo = 1 << p.lo_bits, nhi = (int)p.tw_hi.size() / 2;
-    size_t smem = (size_t)p.H * sizeof(cplx<R>) + (size_t)(nlo + nhi) * sizeof(cplx<R>) +
-                  (size_t)(p.H + 1) * sizeof(R);
-    smem = (smem + 15) & ~(size_t)15;
+    const size_t tab_bytes = (size_t)(nlo + nhi) * sizeof(cplx<R>);
+    size_t work = (size_t)p.H * sizeof(cplx<R>) + (size_t)(p.H + 1) * sizeof(R);   // FFT buffer + pair accumulators
+    work = (work + 15) & ~(size_t)15;
+    size_t smem = (work + tab_bytes + 15) & ~(size_t)15;
     int nthr = ((p.H / 8 + 31) / 32) * 32;
     nthr = std::max(32, std::min(K1_MAX_THREADS, nthr));
     grids->assign(ctx->sh.size(), 0);
@@ -530,19 +531,31 @@ int launch_fft(ta_ctx* ctx, std::vector<int>* grids) {
         Shard& s = ctx->sh[i];
         if (s.natoms == 0) continue;
         CK(cudaSetDevice(s.dev));
-        if (smem > (size_t)s.max_smem)
-            return fail(ctx, TA_ERR_UNSUPPORTED,
-                        "FFT route: T=" + std::to_string(ctx->T) + " needs " + std::to_string(smem) +
-                            " B of shared memory per CTA (limit " + std::to_string(s.max_smem) +
-                            "); use fft=False or precision fp32");
-        CK(cudaFuncSetAttribute(k1_fft_acf<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // buffer + accumulators of one particle: shared memory when they fit, else a per-CTA global work area (any T)
+        const bool in_smem = smem <= (size_t)s.max_smem;
+        const size_t dyn = in_smem ? smem : ((tab_bytes + 15) & ~(size_t)15);
+        if (dyn > (size_t)s.max_smem)
+            return fail(ctx, TA_ERR_UNSUPPORTED, "FFT route: the twiddle tables for T=" + std::to_string(ctx->T) +
+                                                     " do not fit in shared memory; use fft=False");
+        auto kern = in_smem ? k1_fft_acf<R, false> : k1_fft_acf<R, true>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1_fft_acf<R>, nthr, smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nthr, dyn));
         if (occ < 1) return fail(ctx, TA_ERR_UNSUPPORTED, "FFT kernel does not fit on an SM");
+        if (!in_smem) occ = std::min(occ, 2);        // the work areas should stay L2-resident
         int grid = (int)std::min<int64_t>(s.natoms, (int64_t)s.num_sms * occ);
         (*grids)[i] = grid;
         int rc = ensure_partial(ctx, s, (size_t)grid);
         if (rc) return rc;
+        if (!in_smem) {
+            const size_t need = work * (size_t)grid;
+            if (s.win_scratch_bytes < need) {
+                cudaFree(s.win_scratch);
+                s.win_scratch = nullptr; s.win_scratch_bytes = 0;
+                CK(cudaMalloc(&s.win_scratch, need));
+                s.win_scratch_bytes = need;
+            }
+        }
         K1Args<R> a;
         a.t.T = (int)ctx->T; a.t.H = p.H; a.t.L = p.L; a.t.npasses = p.npasses;
         for (int q = 0; q < TA_MAX_PASSES; ++q) a.t.radix[q] = p.radix[q];
@@ -553,19 +566,21 @@ int launch_fft(ta_ctx* ctx, std::vector<int>* grids) {
         a.nlo = nlo; a.nhi = nhi;
         a.partial = s.partial;
         a.D = ctx->D; a.Tld = ctx->Tld;
+        a.scratch = in_smem ? nullptr : (unsigned char*)s.win_scratch;
+        a.scratch_stride = (long long)work;
         CK(cudaEventRecord(s.ev_ka, s.s_compute));
         for (const LaunchRange& rg : take_launch_ranges(s)) {
             if (rg.ready) CK(cudaStreamWaitEvent(s.s_compute, rg.ready, 0));
             a.series = s.series + (size_t)rg.a0 * ctx->D * ctx->Tld;
             a.by_particle = s.by_particle + (size_t)rg.a0 * ctx->Tld;
             a.natoms = (int)rg.n;
-            k1_fft_acf<R><<<(int)std::min<int64_t>(grid, rg.n), nthr, smem, s.s_compute>>>(a);
+            kern<<<(int)std::min<int64_t>(grid, rg.n), nthr, dyn, s.s_compute>>>(a);
             CK(cudaGetLastError());
             ctx->launches++;
         }
         CK(cudaEventRecord(s.ev_kb, s.s_compute));
         s.kernel_timed = true;
-        ctx->k1_threads = nthr; ctx->k1_smem = (int)smem; ctx->k1_grid = grid;
+        ctx->k1_threads = nthr; ctx->k1_smem = (int)dyn; ctx->k1_grid = grid;
     }
     return TA_OK;
 }
