@@ -2,7 +2,7 @@
 """bench.py -- atom-frames/s of the time-correlation hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                    [--workload fft|windowed|helfand] [--atoms A] [--frames T]
+                    [--workload fft|windowed|helfand|helfand_direct] [--atoms A] [--frames T]
 
 Default workload = BASELINE.json configs[3]: VelocityAutocorr fft=True,
 100,000 atoms x 10,000 frames FP64 on one B200 (the largest single-GPU
@@ -58,19 +58,19 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 # algorithmic work per atom-frame (xyz, FP64)
-BYTES_PER_AF = {"fft": 32.0, "windowed": 32.0, "helfand": 56.0, "helfand_fft": 56.0}
+BYTES_PER_AF = {"fft": 32.0, "windowed": 32.0, "helfand": 56.0, "helfand_direct": 56.0}
 FP64_NOMINAL_TFLOPS = 37.0   # 148 SMs x 64 DFMA/clk x 2 x 1.965 GHz (no measured FP64 peak is provided)
 
 DEFAULTS = {          # workload -> (atoms per GPU, frames)   BASELINE.json configs[3], [1], [2]
     "fft": (100_000, 10_000),
     "windowed": (1_000, 2_000),
-    "helfand": (10_000, 5_000),
-    "helfand_fft": (10_000, 5_000),   # opt-in FFT route of the same result (not reference-parity: see DESIGN.md)
+    "helfand": (10_000, 5_000),          # ViscosityHelfand as shipped: S1 - 2 S2 by FFT + exact refinement (K1 + K5 + K6)
+    "helfand_direct": (10_000, 5_000),   # ViscosityHelfand(fft=False): the direct O(T^2) lag sums (K3)
 }
 
 
 def flops_per_af(workload, T, D=3):
-    if workload in ("fft", "helfand_fft"):
+    if workload in ("fft", "helfand"):
         L = 1 << int(np.ceil(np.log2(2 * T - 1)))
         return (D + 1) * 2.5 * L * np.log2(L) / T
     if workload == "windowed":
@@ -179,7 +179,7 @@ def _ref_worker(args):
     rng = np.random.default_rng(seed)
     vel = rng.standard_normal((T, natoms, 3), dtype=np.float32).astype(np.float64)
     t0 = time.perf_counter()
-    if workload == "helfand_fft":
+    if workload == "helfand_direct":
         workload = "helfand"          # the reference has one Helfand route: the O(T^2) lag loop
     if workload == "fft":
         oracle.vacf_fft(vel)
@@ -199,7 +199,7 @@ def cpu_sample_size(workload, T):
     """atoms per worker so that one sample is a few seconds of numpy work."""
     if workload == "fft":
         return max(8, int(4e7 / (T * np.log2(T) * 6)))
-    if workload == "helfand_fft":
+    if workload == "helfand_direct":
         return 64
     if workload == "windowed":
         return max(1, int(1.2e9 / (T * T * 3 * 8)))
@@ -230,7 +230,7 @@ def run_reference(args, rank, world):
     value = sample_af / (ms / 1e3)
     sample = (f"{cores} processes x {per} atoms x {T} frames per step (oracle restatement of the reference's "
               f"numpy/pocketfft path; throughput is linear in atoms)")
-    if workload == "helfand":
+    if workload in ("helfand", "helfand_direct"):
         sample += "; 5 sampled lags extrapolated by sum(T-lag)"
     line = {
         "impl": "reference", "metric": "atom-frames/s", "value": value, "unit": "atom-frames/s", "n_gpus": args.gpus,
@@ -247,7 +247,7 @@ def workload_config(workload, A, T, gpus):
     names = {"fft": "VelocityAutocorr fft=True dim_type=xyz (BASELINE.json configs[3])",
              "windowed": "VelocityAutocorr fft=False dim_type=xyz (BASELINE.json configs[1])",
              "helfand": "ViscosityHelfand dim_type=xyz (BASELINE.json configs[2])",
-             "helfand_fft": "ViscosityHelfand dim_type=xyz fft=True, opt-in FFT route (BASELINE.json configs[2] sizes)"}
+             "helfand_direct": "ViscosityHelfand dim_type=xyz fft=False, direct lag sums (BASELINE.json configs[2])"}
     return {"workload": names[workload], "atoms_per_gpu": A, "atoms_total": A * gpus, "frames": T,
             "dims": 3, "sharding": f"atoms x{gpus}", "l2": "inputs larger than L2 (no flush needed)"
             if A * T * 24 > 2 * 126e6 else "L2 flushed between steps"}
@@ -315,7 +315,7 @@ def run_b200(args, rank, world, local_rank):
     A, T = DEFAULTS[workload]
     A = args.atoms or A
     T = args.frames or T
-    helf = workload in ("helfand", "helfand_fft")
+    helf = workload in ("helfand", "helfand_direct")
 
     # ---- NCCL communicator shared by the ranks (the library owns it)
     nccl_id = None
@@ -347,7 +347,7 @@ def run_b200(args, rank, world, local_rank):
         ctx = None
         dev_arg = [local_rank]
     if helf:
-        ana = ViscosityHelfand(u.atoms, devices=dev_arg, fft=(workload == "helfand_fft"))
+        ana = ViscosityHelfand(u.atoms, devices=dev_arg, fft=("auto" if workload == "helfand" else False))
     else:
         ana = VelocityAutocorr(u.atoms, fft=(workload == "fft"), devices=dev_arg)
 
@@ -374,7 +374,7 @@ def run_b200(args, rank, world, local_rank):
             return ctx.vacf_fft()
         if workload == "windowed":
             return ctx.vacf_windowed()
-        return ctx.helfand(ana._volumes, ana.boltzmann, ana.temp_avg, fft=(workload == "helfand_fft"))
+        return ctx.helfand(ana._volumes, ana.boltzmann, ana.temp_avg, fft=(workload == "helfand"))
 
     need_flush = A * T * 24 <= 2 * 126e6      # inputs do not exceed L2: flush it between steps
     for _ in range(args.warmup):
@@ -413,7 +413,8 @@ def run_b200(args, rank, world, local_rank):
                 "traffic": load_profile_traffic(workload),
                 "kernel": {"fft": k1_kernel_name(ctx.fft_plan_info()) if workload == "fft" else "",
                            "windowed": "k_windowed<double,PRODUCT> (K2)",
-                           "helfand": "k_windowed<double,SQDIFF> (K3)", "helfand_fft": "k1f_fft_acf (K1; K5 follows)"}[workload],
+                           "helfand": "k1f_fft_acf (K1; K5 flags and K6 exact refinement follow)",
+                           "helfand_direct": "k_windowed<double,SQDIFF> (K3)"}[workload],
                 "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": bytes_launch,
                 "kernel_share_of_step": kernel_ms / ms_step,
                 "fp64": {"algorithmic_flop_per_launch": fl, "achieved_tflops": fl / (kernel_ms / 1e3) / 1e12,
@@ -429,7 +430,7 @@ def run_b200(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": "atom-frames/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": {"fft": "VelocityAutocorr(ag, fft=True).run()", "windowed": "VelocityAutocorr(ag, fft=False).run()",
-                            "helfand": "ViscosityHelfand(ag).run()", "helfand_fft": "ViscosityHelfand(ag, fft=True).run()"}[workload]},
+                            "helfand": "ViscosityHelfand(ag).run()", "helfand_direct": "ViscosityHelfand(ag, fft=False).run()"}[workload]},
             "gpu_launches": launches,
             "roofline": roof, "cpu_baseline": cpu, "clocks": sampler.summary(),
             "fft_plan": ctx.fft_plan_info() if workload == "fft" else None,
@@ -449,7 +450,7 @@ def cpu_baseline(workload, T):
     per = cpu_sample_size(workload, T) * 16
     dt = _ref_worker((workload, T, per, 7))
     sample = f"{per} atoms x {T} frames, 1 process (numpy elementwise ops and pocketfft are single-threaded)"
-    if workload == "helfand":
+    if workload in ("helfand", "helfand_direct"):
         sample += "; 5 sampled lags extrapolated by sum(T-lag)"
     return {"value": per * T / dt, "unit": "atom-frames/s", "cores": 1, "kind": "port", "sample": sample}
 
@@ -460,7 +461,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="fft", choices=["fft", "windowed", "helfand", "helfand_fft"])
+    ap.add_argument("--workload", default="fft", choices=["fft", "windowed", "helfand", "helfand_direct"])
     ap.add_argument("--atoms", type=int, default=0, help="atoms per GPU (default: BASELINE config)")
     ap.add_argument("--no-numa-bind", action="store_true",
                     help="do not pin the rank to the CPUs of its GPU's NUMA node before allocating the host trajectory")

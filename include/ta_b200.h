@@ -132,6 +132,9 @@ int ta_flush_l2(ta_ctx* ctx);
 int64_t ta_launch_count(const ta_ctx* ctx);
 int ta_fft_plan_info(const ta_ctx* ctx, int* H, int* npasses, int* radices /*[12]*/,
                      int* threads, int* smem_bytes, int* grid);
+/* (particle, lag) pairs the last ta_helfand_fft evaluated with the exact sum (viscosity.py:212-226) because the
+ * S1 - 2 S2 difference was not good to 1e-10 there; -1: the direct kernel took over the whole call. */
+int64_t ta_helfand_fft_refined(const ta_ctx* ctx);
 
 #ifdef __cplusplus
 }

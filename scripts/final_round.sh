@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q 2>&1 | tail -5
 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_fft.json 2>gpurun_out/bench_fft.err; cut -c1-400 gpurun_out/bench_fft.json
-for w in windowed helfand helfand_fft; do
+for w in windowed helfand helfand_direct; do
   python bench.py --workload $w --steps 5 --warmup 3 > gpurun_out/bench_$w.json 2>gpurun_out/bench_$w.err; cut -c1-300 gpurun_out/bench_$w.json
 done
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2>gpurun_out/bench_reference.err; cut -c1-400 gpurun_out/bench_reference.json

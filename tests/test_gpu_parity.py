@@ -139,36 +139,55 @@ def test_edge_sizes(T, N):
 
 
 # ------------------------------------------------------------------ Helfand
+HELFAND_ROUTES = ["auto", False]      # the default (FFT + exact refinement) and the direct lag sums
+
+
+@pytest.mark.parametrize("route", HELFAND_ROUTES)
 @pytest.mark.parametrize("dim,n_dim", DIMS)
-def test_helfand_random_all_dims(rand_u, dim, n_dim):
+def test_helfand_random_all_dims(rand_u, dim, n_dim, route):
     u, vel, pos, masses = rand_u
     cols, _ = oracle.parse_dim_type(dim)
     vols = np.full(700, float(np.prod(np.float32(BOX[:3]).astype(np.float64))))
     ref_bp, ref_ts = oracle.helfand_msd(_f64(vel)[:, :, cols], _f64(pos)[:, :, cols], masses, vols, 300.0)
-    h = VH(u.atoms, dim_type=dim).run()
+    h = VH(u.atoms, dim_type=dim, fft=route).run()
     assert h.results.timeseries[0] == 0.0 and np.all(h.results.visc_by_particle[0] == 0.0)
     assert_allclose(h.results.timeseries, ref_ts, rtol=TOL64)
     assert_allclose(h.results.visc_by_particle, ref_bp, rtol=TOL64)
 
 
+@pytest.mark.parametrize("route", HELFAND_ROUTES)
 @pytest.mark.parametrize("dim,n_dim", [("xyz", 3), ("yz", 2), ("z", 1)])
-def test_helfand_step_trajectory_known_answer(step_u, dim, n_dim):
-    # reference: tests/test_viscosity.py:167-208 (assert_allclose, default rtol 1e-7)
+def test_helfand_step_trajectory_known_answer(step_u, dim, n_dim, route):
+    # reference: tests/test_viscosity.py:167-208 (assert_allclose, default rtol 1e-7); here at the FP64 bar
     cols, _ = oracle.parse_dim_type(dim)
     vel, pos = ramp_trajectory(5001, 10, 10, 1000)
     expect = oracle.characteristic_poly_helfand(vel[:, :, cols], pos[:, :, cols])
-    h = VH(step_u.atoms, dim_type=dim).run(start=10, stop=1000, step=10)
-    assert_allclose(h.results.timeseries, expect)
+    h = VH(step_u.atoms, dim_type=dim, fft=route).run(start=10, stop=1000, step=10)
+    assert_allclose(h.results.timeseries, expect, rtol=TOL64)
     if dim == "xyz":
         vel, pos = ramp_trajectory(5001)
         expect = oracle.characteristic_poly_helfand(vel, pos)
-        assert_allclose(VH(step_u.atoms).run().results.timeseries, expect)
+        assert_allclose(VH(step_u.atoms, fft=route).run().results.timeseries, expect, rtol=TOL64)
 
 
-def test_notebook_helfand_t10():
+@pytest.mark.parametrize("route", HELFAND_ROUTES)
+def test_notebook_helfand_t10(route):
     vel, pos = ramp_trajectory(10)
     u = make_universe(pos, vel, masses=[16.0], dimensions=[2, 2, 2, 90, 90, 90])
-    assert_allclose(VH(u.atoms).run().results.timeseries * 3, oracle.NOTEBOOK_HELFAND_T10_SUMDIMS, rtol=1e-10)
+    assert_allclose(VH(u.atoms, fft=route).run().results.timeseries * 3, oracle.NOTEBOOK_HELFAND_T10_SUMDIMS, rtol=1e-10)
+
+
+def test_helfand_default_route_falls_back_to_the_direct_sums_beyond_its_length():
+    """fft='auto' on a trajectory longer than the FFT route's finishing kernel holds (T > ~29,000): the direct kernel."""
+    T, N = 30001, 2
+    vel, pos = random_trajectory(T, N, seed=3, with_positions=True, rho=0.9)
+    u = make_universe(pos, vel, masses=[12.0, 16.0], dimensions=BOX)
+    h = VH(u.atoms).run()
+    assert h.fft is False
+    lags = [1, 2, 15000, 30000]
+    ref_bp, _ = oracle.helfand_msd(_f64(vel), _f64(pos), np.array([12.0, 16.0]),
+                                   np.full(T, float(np.prod(np.float32(BOX[:3]).astype(np.float64)))), 300.0, lags=lags)
+    assert_allclose(np.asarray(h.results.visc_by_particle)[lags], ref_bp[lags], rtol=TOL64)
 
 
 # ------------------------------------------------------------------ C ABI direct
@@ -414,7 +433,7 @@ def test_properties_at_config4_full_size():
 def test_properties_at_config2_and_config3_full_size():
     """BASELINE config 2 (windowed VACF, 1,000 x 2,000) and config 3 (Helfand, 10,000 x 5,000) at full size: sampled
     particles against the oracle, windowed == FFT route on all particles, Helfand row 0 == 0, timeseries == particle mean,
-    g -> 2 g gives 4 x the Helfand MSD, opt-in FFT route of the Helfand MSD within its stated 1e-7."""
+    g -> 2 g gives 4 x the Helfand MSD, default route (FFT + exact refinement) == direct lag sums to 1e-10 everywhere."""
     import bench
 
     # ---- config 2
@@ -448,8 +467,10 @@ def test_properties_at_config2_and_config3_full_size():
     lags = [1, 2, 1250, 2500, 3750, 4998, 4999]
     ref_bp, _ = oracle.helfand_msd(_f64(vel[:, pick]), _f64(pos[:, pick]), masses[pick], vols, 300.0, lags=lags)
     assert_allclose(bp[lags][:, pick], ref_bp[lags], rtol=TOL64)
-    hf = VH(u.atoms, fft=True).run()
-    assert_allclose(hf.results.timeseries, ts, rtol=1e-7)
+    hd = VH(u.atoms, fft=False).run()
+    assert h.fft is True and hd.fft is False
+    assert_allclose(hd.results.timeseries, ts, rtol=TOL64)
+    assert_allclose(np.asarray(hd.results.visc_by_particle), bp, rtol=TOL64)
     h2 = VH(make_universe(pos[:, :256], vel[:, :256] * np.float32(2.0), masses=masses[:256], dimensions=BOX).atoms).run()
     assert_allclose(np.asarray(h2.results.visc_by_particle), 4.0 * bp[:, :256], rtol=1e-12)
 
@@ -515,14 +536,14 @@ def test_second_run_on_the_same_object_and_window(rand_u, monkeypatch):
 # ------------------------------------------------------------------ opt-in FFT route of the Helfand MSD (K1 + K5)
 @pytest.mark.parametrize("dim,n_dim", [("xyz", 3), ("xz", 2), ("y", 1)])
 def test_helfand_fft_route_against_exact_route(rand_u, dim, n_dim):
-    """S1 - 2 S2 cancels, so the bar is the stated one (relative error ~ 1e-16 S1/MSD), not 1e-10:
-    1e-7 on every lag for this 700-frame AR(1) trajectory, and row 0 stays exactly 0."""
+    """S1 - 2 S2 cancels; the lags where that costs more than the FP64 bar are re-evaluated exactly (K6), so the FFT
+    route meets rtol 1e-10 on every lag of this 700-frame AR(1) trajectory, and row 0 stays exactly 0."""
     u, vel, pos, masses = rand_u
     exact = VH(u.atoms, dim_type=dim).run()
     fast = VH(u.atoms, dim_type=dim, fft=True).run()
     assert fast.results.timeseries[0] == 0.0 and np.all(fast.results.visc_by_particle[0] == 0.0)
-    assert_allclose(fast.results.timeseries, exact.results.timeseries, rtol=1e-7)
-    assert_allclose(fast.results.visc_by_particle[1:], exact.results.visc_by_particle[1:], rtol=1e-6)
+    assert_allclose(fast.results.timeseries, exact.results.timeseries, rtol=TOL64)
+    assert_allclose(fast.results.visc_by_particle[1:], exact.results.visc_by_particle[1:], rtol=TOL64)
     cols, _ = oracle.parse_dim_type(dim)
     _, ref_ts = oracle.helfand_msd(_f64(vel)[:, :, cols], _f64(pos)[:, :, cols], masses,
                                    np.full(len(vel), np.prod(BOX[:3])), 300.0)
@@ -537,6 +558,49 @@ def test_helfand_fft_route_general_kernel_and_window(rand_u, monkeypatch):
     assert_allclose(fast.results.timeseries, exact.results.timeseries, rtol=1e-7)
     assert_allclose(fast.results.viscosity, exact.results.viscosity, rtol=1e-8)
     assert_allclose(fast.running_viscosity, exact.running_viscosity, rtol=1e-7)
+
+
+def _helfand_case(kind, T, N, seed):
+    """Trajectories that stress the S1 - 2 S2 cancellation differently."""
+    rng = np.random.default_rng(seed)
+    if kind == "white":                       # no correlation: MSD ~ 2 var at every lag, only the last lags are delicate
+        vel = rng.standard_normal((T, N, 3)).astype(np.float32)
+        pos = (10.0 * rng.standard_normal((T, N, 3))).astype(np.float32)
+    elif kind == "smooth":                    # slowly varying g: MSD << sum g^2 at short lags
+        t = np.arange(T)[:, None, None]
+        ph = rng.uniform(0, 6.28, (1, N, 3))
+        vel = (np.sin(2e-3 * t + ph) + 2.0).astype(np.float32)
+        pos = (np.cos(1.3e-3 * t + 2 * ph) + 3.0).astype(np.float32)
+    elif kind == "walk":                      # positions are an unwrapped random walk (the synthetic universe of the survey)
+        vel, pos = random_trajectory(T, N, seed=seed, with_positions=True, rho=0.99)
+    elif kind == "ramp":                      # the reference's step trajectory: v = t, x = t^2 / 2 (g ~ t^3)
+        t = np.arange(T, dtype=np.float64)[:, None, None]
+        vel = np.repeat(np.repeat(t, N, 1), 3, 2).astype(np.float32)
+        pos = np.repeat(np.repeat(t * t / 2, N, 1), 3, 2).astype(np.float32)
+    elif kind == "frozen":                    # most particles do not move at all, a few do
+        vel = np.zeros((T, N, 3), np.float32)
+        pos = np.ones((T, N, 3), np.float32)
+        vel[:, :3] = rng.standard_normal((T, 3, 3)).astype(np.float32)
+    return vel, pos
+
+
+@pytest.mark.parametrize("kind,T,N", [("white", 3000, 40), ("smooth", 3000, 40), ("walk", 5000, 200), ("ramp", 2000, 3),
+                                      ("frozen", 1600, 12), ("white", 10000, 160), ("smooth", 700, 5)])
+def test_helfand_fft_route_with_exact_refinement_meets_the_fp64_bar(kind, T, N):
+    """ViscosityHelfand(fft=True): S1 - 2 S2 where it is good to 1e-10, the exact sum (K6) on the lags it marks, the direct
+    kernel when too much is marked -- against the exact route at the FP64 bar (rtol 1e-10), per particle and in the mean."""
+    vel, pos = _helfand_case(kind, T, N, seed=T + N)
+    masses = np.random.default_rng(1).choice([1.008, 12.011, 15.999], N)
+    u = make_universe(pos, vel, masses=masses, dimensions=BOX)
+    exact = VH(u.atoms).run()
+    fast = VH(u.atoms, fft=True).run()
+    refined = fast._ctx.helfand_fft_refined()
+    e_bp, f_bp = np.asarray(exact.results.visc_by_particle), np.asarray(fast.results.visc_by_particle)
+    assert fast.results.timeseries[0] == 0.0 and np.all(f_bp[0] == 0.0)
+    assert_allclose(f_bp, e_bp, rtol=TOL64, atol=0, err_msg=f"{kind}: refined {refined} of {N * T}")
+    assert_allclose(fast.results.timeseries, exact.results.timeseries, rtol=TOL64)
+    if kind in ("white", "walk"):
+        assert 0 <= refined < 0.02 * N * T            # the FFT did the work
 
 
 # ------------------------------------------------------------------ series longer than shared memory (direct routes)

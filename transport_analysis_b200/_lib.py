@@ -46,6 +46,7 @@ _SIGNATURES = {
     "ta_last_kernel_ms": (c_int, [c_void_p, POINTER(c_float)]),
     "ta_flush_l2": (c_int, [c_void_p]),
     "ta_launch_count": (c_int64, [c_void_p]),
+    "ta_helfand_fft_refined": (c_int64, [c_void_p]),
     "ta_fft_plan_info": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int),
                                  POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
 }
@@ -54,8 +55,15 @@ EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 _lib = None
 
 
+TA_ERR_UNSUPPORTED = -4   # include/ta_b200.h
+
+
 class BackendError(RuntimeError):
     """A libta_b200 call failed (the message carries ta_last_error())."""
+
+
+class UnsupportedError(BackendError):
+    """TA_ERR_UNSUPPORTED: the requested route does not serve this problem size / precision."""
 
 
 def load_library(path: str | None = None) -> ctypes.CDLL:
@@ -124,7 +132,8 @@ class Context:
     # -- plumbing ---------------------------------------------------------
     def _check(self, rc: int, what: str):
         if rc != 0:
-            raise BackendError(f"{what} failed ({rc}): {self._lib.ta_last_error(self._h).decode()}")
+            cls = UnsupportedError if rc == TA_ERR_UNSUPPORTED else BackendError
+            raise cls(f"{what} failed ({rc}): {self._lib.ta_last_error(self._h).decode()}")
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -207,8 +216,8 @@ class Context:
         return ts
 
     def helfand(self, volumes, boltzmann: float, temp_avg: float, fft: bool = False) -> np.ndarray:
-        """``fft=False``: the direct windowed MSD (kernel K3, reference parity).  ``fft=True``: the
-        opt-in O(T log T) route S1 - 2 S2 (kernels K1 + K5; cancellation-limited accuracy)."""
+        """``fft=False``: the direct windowed MSD (kernel K3).  ``fft=True``: the O(T log T) route S1 - 2 S2 with exact
+        re-evaluation of the lags where the difference cancels (kernels K1 + K5 + K6).  Both meet the 1e-10 bar."""
         vol = np.ascontiguousarray(volumes, dtype=np.float64)
         if vol.shape != (self.T,):
             raise ValueError("volumes must have one entry per analysed frame")
@@ -252,6 +261,10 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self._lib.ta_launch_count(self._h))
+
+    def helfand_fft_refined(self) -> int:
+        """(particle, lag) pairs the last FFT-route Helfand call evaluated exactly; -1 if the direct kernel did it all."""
+        return int(self._lib.ta_helfand_fft_refined(self._h))
 
     def fft_plan_info(self) -> dict:
         H, npz, thr, smem, grid = c_int(), c_int(), c_int(), c_int(), c_int()

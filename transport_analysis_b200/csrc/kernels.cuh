@@ -355,23 +355,32 @@ k_windowed(const WinArgs args) {
 struct HelfandFftArgs {
     const double* series;   // [natoms][D][Tld]
     double* by_particle;    // [natoms][Tld]  in: sum_d acf_d ; out: viscosity function
-    double* partial;        // [gridDim.x][Tld]
+    double* partial;        // [gridDim.x][Tld]   (K6)
     int natoms, D, T;
     long long Tld;
     double denom;           // 2 kB <V> temp_avg
+    uint32_t* flags;        // [natoms][nwords]  bit k of a particle: lag k needs the exact evaluation
+    int nwords;             // ceil(T / 32)
+    unsigned long long* nflagged;   // total number of flagged (particle, lag) pairs
+    double thr;             // a lag is flagged when its un-normalised MSD is below thr * sum_i sum_d g^2
 };
 
 constexpr int K5_THREADS = 256;
 
+// K5: S1[k] - 2 S2[k] per particle.  Both terms are of the size of sum g^2 and carry rounding errors of that size
+// (C eps sum g^2: the FFT autocorrelation and the prefix sums), so the difference is only as accurate as
+// C eps sum g^2 / MSD[k] relative.  Lags whose MSD is too small for the 1e-10 bar (short lags of smooth series, the last
+// lags of any series) are marked in a per-particle bitmap and evaluated exactly by K6.
 __global__ void __launch_bounds__(K5_THREADS)
 k5_helfand_fft_finish(const HelfandFftArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* P = reinterpret_cast<double*>(smem_raw);   // P[j] = sum_{i<j} q[i], j = 0..T
     __shared__ double wsum[K5_THREADS / 32];
+    __shared__ unsigned cta_flagged;
     const int T = a.T, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int seg = (T + K5_THREADS - 1) / K5_THREADS;
     const int lo = min(T, tid * seg), hi = min(T, lo + seg);
-    double* partial = a.partial + (size_t)blockIdx.x * a.Tld;
+    if (tid == 0) cta_flagged = 0;
     for (int n = blockIdx.x; n < a.natoms; n += gridDim.x) {
         const double* ser = a.series + (size_t)n * a.D * a.Tld;
         __syncthreads();   // previous particle's P fully consumed
@@ -398,16 +407,79 @@ k5_helfand_fft_finish(const HelfandFftArgs a) {
         for (int i = lo; i < hi; ++i) P[i + 1] += base;
         __syncthreads();
         double* row = a.by_particle + (size_t)n * a.Tld;
+        uint32_t* fl = a.flags + (size_t)n * a.nwords;
         const double tot = P[T];
-        for (int k = tid; k < T; k += K5_THREADS) {
-            double val = 0.0;                                   // lag 0 stays exactly 0 (viscosity.py:207-210)
-            if (k > 0) {
-                const double s1 = P[T - k] + (tot - P[k]);
-                val = (s1 / (double)(T - k) - 2.0 * row[k]) / (double)a.D / a.denom;
+        const double floor_msd = a.thr * tot;
+        unsigned mine = 0;
+        for (int k0 = 0; k0 < T; k0 += K5_THREADS) {            // uniform trip count: the ballot needs whole warps
+            const int k = k0 + tid;
+            bool flag = false;
+            if (k < T) {
+                double val = 0.0;                               // lag 0 stays exactly 0 (viscosity.py:207-210)
+                if (k > 0) {
+                    const double s1 = P[T - k] + (tot - P[k]);
+                    const double nk = (double)(T - k);
+                    const double msd = s1 - 2.0 * row[k] * nk;  // un-normalised, what the threshold is about
+                    flag = !(msd >= floor_msd);                 // also catches a NaN
+                    val = (s1 / nk - 2.0 * row[k]) / (double)a.D / a.denom;
+                }
+                row[k] = val;
             }
-            row[k] = val;
-            partial[k] += val;
+            const unsigned m = __ballot_sync(0xffffffffu, flag);
+            if (lane == 0 && k < T) { fl[k >> 5] = m; mine += __popc(m); }
         }
+        if (lane == 0 && mine) atomicAdd(&cta_flagged, mine);
+    }
+    __syncthreads();
+    if (tid == 0 && cta_flagged) atomicAdd(a.nflagged, (unsigned long long)cta_flagged);
+}
+
+// K6: exact evaluation of the flagged lags, sum_d sum_i (g_d[i] - g_d[i+k])^2 (viscosity.py:212-226; one warp per lag, lanes
+// stride the origins, fixed-order reduction), then the particle sum of the finished rows into the per-CTA partial row.
+__global__ void __launch_bounds__(K5_THREADS)
+k6_helfand_refine(const HelfandFftArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* g = reinterpret_cast<double*>(smem_raw);   // one series of the particle
+    __shared__ int any_flag;
+    const int T = a.T, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = K5_THREADS / 32;
+    double* partial = a.partial + (size_t)blockIdx.x * a.Tld;
+    for (int n = blockIdx.x; n < a.natoms; n += gridDim.x) {
+        const double* ser = a.series + (size_t)n * a.D * a.Tld;
+        double* row = a.by_particle + (size_t)n * a.Tld;
+        const uint32_t* fl = a.flags + (size_t)n * a.nwords;
+        __syncthreads();
+        if (tid == 0) any_flag = 0;
+        __syncthreads();
+        int has = 0;
+        for (int w = tid; w < a.nwords; w += K5_THREADS) has |= (fl[w] != 0u);
+        if (has) any_flag = 1;
+        __syncthreads();
+        if (any_flag) {
+            for (int d = 0; d < a.D; ++d) {
+                __syncthreads();
+                for (int i = tid; i < T; i += K5_THREADS) g[i] = ser[(size_t)d * a.Tld + i];
+                __syncthreads();
+                // flagged lags of this particle, dealt to the warps word by word
+                for (int w = warp; w < a.nwords; w += NW) {
+                    uint32_t m = fl[w];
+                    while (m) {
+                        const int k = (w << 5) + __ffs(m) - 1;
+                        m &= m - 1;
+                        double acc = 0.0;
+                        for (int i = lane; i < T - k; i += 32) { const double df = g[i] - g[i + k]; acc = fma(df, df, acc); }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                        if (lane == 0) {
+                            const double t = (d == 0 ? 0.0 : row[k]) + acc;
+                            row[k] = (d == a.D - 1) ? t / (double)(T - k) / (double)a.D / a.denom : t;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        for (int k = tid; k < T; k += K5_THREADS) partial[k] += row[k];
     }
 }
 

@@ -129,6 +129,9 @@ struct Shard {
     uint32_t* e_map = nullptr;
     void* e_wbase = nullptr;
     unsigned* e_slots = nullptr;        // [1024] per-SM CTA arrival counters (stagger of co-resident CTAs)
+    // FFT route of the Helfand MSD: per-particle bitmaps of the lags that need the exact evaluation (+ a counter)
+    uint32_t* hflags = nullptr;
+    size_t hflags_bytes = 0;
 };
 
 }  // namespace
@@ -161,6 +164,7 @@ struct ta_ctx {
     int k1_threads = 0, k1_smem = 0, k1_grid = 0;
     std::vector<double> host_ts;
     int64_t launches = 0;
+    long long helfand_fft_flagged = 0;   // (particle, lag) pairs the last ta_helfand_fft evaluated exactly; -1: all (K3 took over)
 };
 
 namespace {
@@ -223,6 +227,7 @@ void free_problem(ta_ctx* c) {
         cudaFree(s.e_map); s.e_map = nullptr;
         cudaFree(s.e_wbase); s.e_wbase = nullptr;
         cudaFree(s.e_slots); s.e_slots = nullptr;
+        cudaFree(s.hflags); s.hflags = nullptr; s.hflags_bytes = 0;
     }
     for (int i = 0; i < kNumSlabs; ++i) {
         if (c->slab[i]) cudaFreeHost(c->slab[i]);
@@ -1219,24 +1224,79 @@ int ta_helfand_fft(ta_ctx* ctx, const double* volumes, double boltzmann, double 
     std::vector<int> grids;
     rc = (ctx->fast_r1 > 0 || ctx->fast_r8 > 0) ? launch_fft_fast(ctx, &grids) : launch_fft<double>(ctx, &grids);   // by_particle = sum_d acf_d
     if (rc) return rc;
+    // K5 forms S1 - 2 S2 and marks the lags whose result is not good to 1e-10 (cancellation); K6 evaluates those exactly and
+    // sums the particles.  thr = C eps / tol: C = 100 + T / 100 bounds the error constant of S1 - 2 S2 (FFT autocorrelation +
+    // prefix sums; measured 11 - 18 on random, random-walk and ramp moments, 15 at T = 3,000 and 33 at T = 10,000 on smooth
+    // ones: scripts/helfand_fft_error_constant.py), tol = 2e-11 leaves a factor 5 to the 1e-10 bar on top of that.
+    // If a shard has more than 2 % of its (particle, lag) pairs marked, the direct kernel K3 does that shard instead.
+    const char* thr_env = getenv("TA_B200_HELFAND_FFT_THR");
+    const double thr = thr_env ? atof(thr_env) : (100.0 + (double)ctx->T / 100.0) * 1.1102230246251565e-16 / 2e-11;
     const size_t smem = ((size_t)ctx->T + 1) * sizeof(double);
+    const int nwords = (int)((ctx->T + 31) / 32);
+    std::vector<unsigned long long> nflag(ctx->sh.size(), 0);
     for (size_t i = 0; i < ctx->sh.size(); ++i) {
         Shard& s = ctx->sh[i];
         if (s.natoms == 0) continue;
         CK(cudaSetDevice(s.dev));
         if (smem > (size_t)s.max_smem)
             return fail(ctx, TA_ERR_UNSUPPORTED, "FFT Helfand route: T=" + std::to_string(ctx->T) + " does not fit shared memory");
+        const size_t fbytes = (size_t)s.natoms * nwords * sizeof(uint32_t) + 16;
+        if (s.hflags_bytes < fbytes) {
+            cudaFree(s.hflags);
+            s.hflags = nullptr; s.hflags_bytes = 0;
+            CK(cudaMalloc((void**)&s.hflags, fbytes));
+            s.hflags_bytes = fbytes;
+        }
+        unsigned long long* counter = reinterpret_cast<unsigned long long*>(
+            reinterpret_cast<unsigned char*>(s.hflags) + ((fbytes - 16 + 7) & ~(size_t)7));
+        CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s.s_compute));
         CK(cudaFuncSetAttribute(k5_helfand_fft_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k6_helfand_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k5_helfand_fft_finish, K5_THREADS, smem));
         if (occ < 1) return fail(ctx, TA_ERR_UNSUPPORTED, "K5 does not fit on an SM");
+        const int grid = (int)std::min<int64_t>(s.natoms, (int64_t)s.num_sms * occ);
+        grids[i] = grid;
+        HelfandFftArgs a;
+        a.series = s.series; a.by_particle = s.by_particle; a.partial = s.partial;
+        a.natoms = (int)s.natoms; a.D = ctx->D; a.T = (int)ctx->T; a.Tld = ctx->Tld; a.denom = denom;
+        a.flags = s.hflags; a.nwords = nwords; a.nflagged = counter; a.thr = thr;
+        k5_helfand_fft_finish<<<grid, K5_THREADS, smem, s.s_compute>>>(a);
+        CK(cudaGetLastError());
+        ctx->launches++;
+        CK(cudaMemcpyAsync(&nflag[i], counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.s_compute));
+    }
+    bool need_k3 = false;
+    for (size_t i = 0; i < ctx->sh.size(); ++i) {
+        Shard& s = ctx->sh[i];
+        if (s.natoms == 0) continue;
+        CK(cudaSetDevice(s.dev));
+        CK(cudaStreamSynchronize(s.s_compute));
+        ctx->helfand_fft_flagged = (i == 0 ? 0 : ctx->helfand_fft_flagged) + (long long)nflag[i];
+        if ((double)nflag[i] > 0.02 * (double)s.natoms * (double)ctx->T) need_k3 = true;
+    }
+    if (need_k3) {
+        // too much of the result needs the exact evaluation (series that barely move): the direct kernel does it all
+        ctx->helfand_fft_flagged = -1;
+        rc = launch_windowed<double, TA_WIN_SQDIFF>(ctx, denom, &grids);
+        if (rc) return rc;
+        return finish_timeseries(ctx, grids, ts_out);
+    }
+    for (size_t i = 0; i < ctx->sh.size(); ++i) {
+        Shard& s = ctx->sh[i];
+        if (s.natoms == 0) continue;
+        CK(cudaSetDevice(s.dev));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k6_helfand_refine, K5_THREADS, smem));
+        if (occ < 1) return fail(ctx, TA_ERR_UNSUPPORTED, "K6 does not fit on an SM");
         const int grid = (int)std::min<int64_t>(s.natoms, (int64_t)s.num_sms * occ);
         grids[i] = grid;
         if ((rc = ensure_partial(ctx, s, (size_t)grid))) return rc;    // drops K1's partial rows (sums of the ACF)
         HelfandFftArgs a;
         a.series = s.series; a.by_particle = s.by_particle; a.partial = s.partial;
         a.natoms = (int)s.natoms; a.D = ctx->D; a.T = (int)ctx->T; a.Tld = ctx->Tld; a.denom = denom;
-        k5_helfand_fft_finish<<<grid, K5_THREADS, smem, s.s_compute>>>(a);
+        a.flags = s.hflags; a.nwords = nwords; a.nflagged = nullptr; a.thr = thr;
+        k6_helfand_refine<<<grid, K5_THREADS, smem, s.s_compute>>>(a);
         CK(cudaGetLastError());
         ctx->launches++;
     }
@@ -1333,6 +1393,8 @@ int ta_last_kernel_ms(ta_ctx* ctx, float* ms) {
 }
 
 int64_t ta_launch_count(const ta_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int64_t ta_helfand_fft_refined(const ta_ctx* ctx) { return ctx ? ctx->helfand_fft_flagged : 0; }
 
 int ta_fft_plan_info(const ta_ctx* ctx, int* H, int* npasses, int* radices, int* threads, int* smem_bytes, int* grid) {
     if (!ctx) return TA_ERR_INVALID;

@@ -6,8 +6,11 @@ transport_analysis/viscosity.py:26-272): same constructor arguments
 step)``, ``results.timeseries`` / ``results.visc_by_particle`` /
 ``results.viscosity``.  Velocities and positions are staged together; the
 Helfand moment ``g = (m*v)*x`` is formed on the device while staging (kernel
-K0) and ``_conclude`` is one call into ``libta_b200.so`` (kernel K3: direct
-windowed mean-squared displacement of ``g``).  There is no CPU fallback.
+K0) and ``_conclude`` is one call into ``libta_b200.so``: the mean-squared
+displacement of ``g`` as ``S1 - 2 S2`` with the FFT autocorrelation kernel and
+an exact re-evaluation of every lag where that difference is not good to 1e-10
+(kernels K1 + K5 + K6), or the direct windowed sums (kernel K3).  There is no
+CPU fallback.
 """
 from __future__ import annotations
 
@@ -33,16 +36,18 @@ class ViscosityHelfand(AnalysisBase):
     Extra keyword arguments: ``precision``, ``devices``, ``max_eager_bytes``
     as for :class:`~transport_analysis_b200.velocityautocorr.VelocityAutocorr`, and
 
-    ``fft``  ``False`` (default): the direct O(T^2) lag sums of the reference (1e-10 parity).
-             ``True``: opt-in O(T log T) route ``sum (g_i - g_{i+k})^2 = S1[k] - 2 S2[k]`` with ``S2``
-             from the FFT autocorrelation kernel -- the idea the reference's dev notebook leaves for
-             later (docs/tutorials/helfand_dev_toy_system.ipynb:134).  The difference cancels: the
-             relative error is about ``1e-16 * S1/MSD`` (~1e-8 at lag 1 for 5,000-frame random-walk
-             moments, far smaller at long lags), so it is not held to the 1e-10 bar.
+    ``fft``  ``"auto"`` (default): the O(T log T) route where it applies (FP64, T <~ 29,000), else the direct sums.
+             ``True``: the O(T log T) route ``sum (g_i - g_{i+k})^2 = S1[k] - 2 S2[k]`` with ``S2`` from the FFT
+             autocorrelation kernel -- the idea the reference's dev notebook leaves for later
+             (docs/tutorials/helfand_dev_toy_system.ipynb:134).  The difference cancels (relative error about
+             ``30 eps sum(g^2) / MSD[k]``: 1e-9 at the short lags of smooth moments), so every lag whose MSD is below
+             ``thr * sum(g^2)`` is re-evaluated with the exact sum of the reference (viscosity.py:212-226); if more than
+             2 % of a shard's lags need that, the direct kernel does the shard.  Meets the same 1e-10 bar as
+             ``False``: the direct O(T^2) lag sums of the reference for every lag.
     """
 
     def __init__(self, atomgroup, temp_avg=300.0, dim_type="xyz", linear_fit_window=None,
-                 precision="fp64", devices=None, max_eager_bytes=1 << 30, fft=False, **kwargs):
+                 precision="fp64", devices=None, max_eager_bytes=1 << 30, fft="auto", **kwargs):
         super().__init__(atomgroup.universe.trajectory, **kwargs)
 
         if isinstance(atomgroup, UpdatingAtomGroup):
@@ -55,9 +60,12 @@ class ViscosityHelfand(AnalysisBase):
         if precision not in ("fp64", "fp32"):
             raise ValueError("precision must be 'fp64' or 'fp32'")
         self.precision = precision
-        self.fft = bool(fft)
-        if self.fft and precision != "fp64":
+        if fft not in (True, False, "auto"):
+            raise ValueError("fft must be True, False or 'auto'")
+        if fft is True and precision != "fp64":
             raise ValueError("fft=True (FFT route of the Helfand MSD) needs precision='fp64'")
+        self.fft = (precision == "fp64") if fft == "auto" else bool(fft)
+        self._fft_auto = fft == "auto"
         self._devices = resolve_devices(devices)
         self._max_eager_bytes = int(max_eager_bytes)
 
@@ -101,7 +109,13 @@ class ViscosityHelfand(AnalysisBase):
         self._stager.finish()
         self._ctx = self._stager.ctx
         self._vol_avg = np.average(self._volumes)
-        self.results.timeseries = self._ctx.helfand(self._volumes, self.boltzmann, self.temp_avg, fft=self.fft)
+        try:
+            self.results.timeseries = self._ctx.helfand(self._volumes, self.boltzmann, self.temp_avg, fft=self.fft)
+        except _lib.UnsupportedError:
+            if not (self.fft and self._fft_auto):
+                raise
+            self.fft = False          # longer than the FFT route's finishing kernel holds: the direct sums serve any T
+            self.results.timeseries = self._ctx.helfand(self._volumes, self.boltzmann, self.temp_avg, fft=False)
         nbytes = 8 * self.n_frames * self.n_particles
         if nbytes <= self._max_eager_bytes:
             self.results.visc_by_particle = self._ctx.fetch_by_particle()
