@@ -16,9 +16,10 @@
  *   ta_vacf_fft               VelocityAutocorr._conclude_fft transport_analysis/velocityautocorr.py:208-215
  *                             + tidynamics.acf (un-vendored dependency, call site :211-213)
  *   ta_vacf_windowed          VelocityAutocorr._conclude_simple transport_analysis/velocityautocorr.py:217-238
- *   ta_helfand                ViscosityHelfand._conclude     transport_analysis/viscosity.py:201-233
- *   ta_helfand_fft            the same result by an FFT route (opt-in; not in the shipped reference,
- *                             flagged as future work in docs/tutorials/helfand_dev_toy_system.ipynb:134)
+ *   ta_helfand                ViscosityHelfand._conclude     transport_analysis/viscosity.py:201-233 (direct lag sums)
+ *   ta_helfand_fft            the same, O(T log T): S1 - 2 S2 by FFT (the idea flagged as future work in
+ *                             docs/tutorials/helfand_dev_toy_system.ipynb:134) with the reference's own sum
+ *                             (viscosity.py:212-226) on every lag where that difference is not good to 1e-10
  *   ta_fetch_by_particle      results.vacf_by_particle / results.visc_by_particle
  *                             (velocityautocorr.py:145-147, viscosity.py:117-119, :229-231)
  *
@@ -108,10 +109,12 @@ int ta_vacf_fft(ta_ctx* ctx, double* ts_out);
 int ta_vacf_windowed(ta_ctx* ctx, double* ts_out);
 int ta_helfand(ta_ctx* ctx, const double* volumes /*[T]*/, double boltzmann, double temp_avg,
                double* ts_out);
-/* Opt-in O(T log T) route to the same Helfand MSD: sum (g[i]-g[i+k])^2 = S1[k] - 2 S2[k] with S2 from
- * the FFT autocorrelation kernel (idea noted in docs/tutorials/helfand_dev_toy_system.ipynb:134).
- * The difference cancels: relative error ~ 1e-16 * S1/MSD, largest at small lags (about 1e-8 for
- * T = 5,000 random-walk moments), so it is NOT the default and not held to the 1e-10 bar. */
+/* O(T log T) route to the same Helfand MSD: sum (g[i]-g[i+k])^2 = S1[k] - 2 S2[k] with S2 from the FFT
+ * autocorrelation kernel (idea noted in docs/tutorials/helfand_dev_toy_system.ipynb:134).  The difference
+ * cancels (relative error ~ 30 eps sum g^2 / MSD[k]), so every lag whose MSD is below thr * sum g^2 is
+ * re-evaluated with the exact sum of viscosity.py:212-226; when more than 2 % of a shard's lags need that the
+ * direct kernel of ta_helfand does the shard.  Same 1e-10 bar as ta_helfand; FP64 only; TA_ERR_UNSUPPORTED
+ * for T beyond ~29,000 (callers fall back to ta_helfand, which serves any T). */
 int ta_helfand_fft(ta_ctx* ctx, const double* volumes /*[T]*/, double boltzmann, double temp_avg,
                    double* ts_out);
 int ta_fetch_by_particle(ta_ctx* ctx, int64_t atom0, int64_t natoms, int layout, double* out);
