@@ -365,7 +365,7 @@ struct HelfandFftArgs {
     double thr;             // a lag is flagged when its un-normalised MSD is below thr * sum_i sum_d g^2
 };
 
-constexpr int K5_THREADS = 256;
+constexpr int K5_THREADS = 1024;
 
 // K5: S1[k] - 2 S2[k] per particle.  Both terms are of the size of sum g^2 and carry rounding errors of that size
 // (C eps sum g^2: the FFT autocorrelation and the prefix sums), so the difference is only as accurate as
@@ -381,14 +381,22 @@ k5_helfand_fft_finish(const HelfandFftArgs a) {
     const int seg = (T + K5_THREADS - 1) / K5_THREADS;
     const int lo = min(T, tid * seg), hi = min(T, lo + seg);
     if (tid == 0) cta_flagged = 0;
+    double* partial = a.partial + (size_t)blockIdx.x * a.Tld;   // particle sum of the rows as K5 leaves them; K6 corrects it
     for (int n = blockIdx.x; n < a.natoms; n += gridDim.x) {
         const double* ser = a.series + (size_t)n * a.D * a.Tld;
         __syncthreads();   // previous particle's P fully consumed
         // q[i] into P[i + 1] (coalesced), then a three-level inclusive scan
-        for (int i = tid; i < T; i += K5_THREADS) {
-            double q = 0.0;
-            for (int d = 0; d < a.D; ++d) { const double g = ser[(size_t)d * a.Tld + i]; q += g * g; }
-            P[i + 1] = q;
+        for (int i0 = 0; i0 < T; i0 += 4 * K5_THREADS) {       // four samples per thread in flight
+            double q[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int d = 0; d < a.D; ++d) {
+                double gv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const int i = i0 + j * K5_THREADS + tid; gv[j] = i < T ? ser[(size_t)d * a.Tld + i] : 0.0; }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) q[j] = fma(gv[j], gv[j], q[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const int i = i0 + j * K5_THREADS + tid; if (i < T) P[i + 1] = q[j]; }
         }
         if (tid == 0) P[0] = 0.0;
         __syncthreads();
@@ -410,23 +418,38 @@ k5_helfand_fft_finish(const HelfandFftArgs a) {
         uint32_t* fl = a.flags + (size_t)n * a.nwords;
         const double tot = P[T];
         const double floor_msd = a.thr * tot;
+        const double cscale = 1.0 / ((double)a.D * a.denom);
         unsigned mine = 0;
-        for (int k0 = 0; k0 < T; k0 += K5_THREADS) {            // uniform trip count: the ballot needs whole warps
-            const int k = k0 + tid;
-            bool flag = false;
-            if (k < T) {
-                double val = 0.0;                               // lag 0 stays exactly 0 (viscosity.py:207-210)
-                if (k > 0) {
-                    const double s1 = P[T - k] + (tot - P[k]);
-                    const double nk = (double)(T - k);
-                    const double msd = s1 - 2.0 * row[k] * nk;  // un-normalised, what the threshold is about
-                    flag = !(msd >= floor_msd);                 // also catches a NaN
-                    val = (s1 / nk - 2.0 * row[k]) / (double)a.D / a.denom;
-                }
-                row[k] = val;
+        // lags k = k0 + tid, in batches of KB: the global loads of a batch (row, partial) are issued together;
+        // uniform trip count (the ballot needs whole warps)
+        constexpr int KB = 4;
+        for (int k0 = 0; k0 < T; k0 += KB * K5_THREADS) {
+            double r[KB], pa[KB];
+#pragma unroll
+            for (int j = 0; j < KB; ++j) {
+                const int k = k0 + j * K5_THREADS + tid;
+                r[j] = k < T ? row[k] : 0.0;
+                pa[j] = k < T ? partial[k] : 0.0;
             }
-            const unsigned m = __ballot_sync(0xffffffffu, flag);
-            if (lane == 0 && k < T) { fl[k >> 5] = m; mine += __popc(m); }
+#pragma unroll
+            for (int j = 0; j < KB; ++j) {
+                const int k = k0 + j * K5_THREADS + tid;
+                bool flag = false;
+                if (k < T) {
+                    double val = 0.0;                           // lag 0 stays exactly 0 (viscosity.py:207-210)
+                    if (k > 0) {
+                        const double s1 = P[T - k] + (tot - P[k]);
+                        const double nk = (double)(T - k);
+                        const double msd = s1 - 2.0 * r[j] * nk;    // un-normalised, what the threshold is about
+                        flag = !(msd >= floor_msd);                 // also catches a NaN
+                        val = (s1 / nk - 2.0 * r[j]) * cscale;
+                    }
+                    row[k] = val;
+                    partial[k] = pa[j] + val;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, flag);
+                if (lane == 0 && k < T) { fl[k >> 5] = m; mine += __popc(m); }
+            }
         }
         if (lane == 0 && mine) atomicAdd(&cta_flagged, mine);
     }
@@ -435,12 +458,15 @@ k5_helfand_fft_finish(const HelfandFftArgs a) {
 }
 
 // K6: exact evaluation of the flagged lags, sum_d sum_i (g_d[i] - g_d[i+k])^2 (viscosity.py:212-226; one warp per lag, lanes
-// stride the origins, fixed-order reduction), then the particle sum of the finished rows into the per-CTA partial row.
+// stride the origins, fixed-order reduction); the row takes the exact value and the per-CTA partial row (the particle sum K5
+// formed, same CTA -> particle map) the difference.  A particle whose flagged lags add up to little work (the usual case: the
+// last one or two lags, a handful of origins) reads its few samples straight from global memory; otherwise its series are
+// staged in shared memory one dimension at a time.
 __global__ void __launch_bounds__(K5_THREADS)
 k6_helfand_refine(const HelfandFftArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* g = reinterpret_cast<double*>(smem_raw);   // one series of the particle
-    __shared__ int any_flag;
+    double* g = reinterpret_cast<double*>(smem_raw);   // one series of the particle (staged particles only)
+    __shared__ unsigned long long work_sum;
     const int T = a.T, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = K5_THREADS / 32;
     double* partial = a.partial + (size_t)blockIdx.x * a.Tld;
@@ -449,37 +475,49 @@ k6_helfand_refine(const HelfandFftArgs a) {
         double* row = a.by_particle + (size_t)n * a.Tld;
         const uint32_t* fl = a.flags + (size_t)n * a.nwords;
         __syncthreads();
-        if (tid == 0) any_flag = 0;
+        if (tid == 0) work_sum = 0ull;
         __syncthreads();
-        int has = 0;
-        for (int w = tid; w < a.nwords; w += K5_THREADS) has |= (fl[w] != 0u);
-        if (has) any_flag = 1;
+        unsigned long long w_mine = 0ull;               // origins to visit: sum over flagged lags of (T - k)
+        for (int w = tid; w < a.nwords; w += K5_THREADS) {
+            uint32_t m = fl[w];
+            while (m) { const int k = (w << 5) + __ffs(m) - 1; m &= m - 1; w_mine += (unsigned long long)(T - k); }
+        }
+        if (w_mine) atomicAdd(&work_sum, w_mine);
         __syncthreads();
-        if (any_flag) {
-            for (int d = 0; d < a.D; ++d) {
+        const unsigned long long work = work_sum;
+        if (work == 0ull) continue;
+        const bool staged = work > 4ull * (unsigned long long)T;
+        for (int d = 0; d < a.D; ++d) {
+            const double* sd = ser + (size_t)d * a.Tld;
+            if (staged) {
                 __syncthreads();
-                for (int i = tid; i < T; i += K5_THREADS) g[i] = ser[(size_t)d * a.Tld + i];
+                for (int i = tid; i < T; i += K5_THREADS) g[i] = sd[i];
                 __syncthreads();
-                // flagged lags of this particle, dealt to the warps word by word
-                for (int w = warp; w < a.nwords; w += NW) {
-                    uint32_t m = fl[w];
-                    while (m) {
-                        const int k = (w << 5) + __ffs(m) - 1;
-                        m &= m - 1;
-                        double acc = 0.0;
-                        for (int i = lane; i < T - k; i += 32) { const double df = g[i] - g[i + k]; acc = fma(df, df, acc); }
+            }
+            const double* src = staged ? g : sd;
+            for (int w = warp; w < a.nwords; w += NW) {  // flagged lags of this particle, dealt to the warps word by word
+                uint32_t m = fl[w];
+                while (m) {
+                    const int k = (w << 5) + __ffs(m) - 1;
+                    m &= m - 1;
+                    double acc = 0.0;
+                    for (int i = lane; i < T - k; i += 32) { const double df = src[i] - src[i + k]; acc = fma(df, df, acc); }
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                        if (lane == 0) {
-                            const double t = (d == 0 ? 0.0 : row[k]) + acc;
-                            row[k] = (d == a.D - 1) ? t / (double)(T - k) / (double)a.D / a.denom : t;
+                    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    if (lane == 0) {
+                        // the running exact sum over the dimensions waits in the row itself; what K5 had put there leaves
+                        // the particle sum first and the exact value enters it after the last dimension
+                        if (d == 0) { partial[k] -= row[k]; row[k] = acc; }
+                        else row[k] += acc;
+                        if (d == a.D - 1) {
+                            const double e = row[k] / (double)(T - k) / (double)a.D / a.denom;
+                            row[k] = e;
+                            partial[k] += e;
                         }
                     }
                 }
             }
-            __syncthreads();
         }
-        for (int k = tid; k < T; k += K5_THREADS) partial[k] += row[k];
     }
 }
 

@@ -1255,8 +1255,13 @@ int ta_helfand_fft(ta_ctx* ctx, const double* volumes, double boltzmann, double 
         int occ = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k5_helfand_fft_finish, K5_THREADS, smem));
         if (occ < 1) return fail(ctx, TA_ERR_UNSUPPORTED, "K5 does not fit on an SM");
-        const int grid = (int)std::min<int64_t>(s.natoms, (int64_t)s.num_sms * occ);
+        int occ6 = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ6, k6_helfand_refine, K5_THREADS, smem));
+        if (occ6 < 1) return fail(ctx, TA_ERR_UNSUPPORTED, "K6 does not fit on an SM");
+        // one grid for K5 and K6: K6 corrects the per-CTA partial rows K5 wrote, with the same CTA -> particle map
+        const int grid = (int)std::min<int64_t>(s.natoms, (int64_t)s.num_sms * std::min(occ, occ6));
         grids[i] = grid;
+        if ((rc = ensure_partial(ctx, s, (size_t)grid))) return rc;    // drops K1's partial rows (sums of the ACF)
         HelfandFftArgs a;
         a.series = s.series; a.by_particle = s.by_particle; a.partial = s.partial;
         a.natoms = (int)s.natoms; a.D = ctx->D; a.T = (int)ctx->T; a.Tld = ctx->Tld; a.denom = denom;
@@ -1286,12 +1291,8 @@ int ta_helfand_fft(ta_ctx* ctx, const double* volumes, double boltzmann, double 
         Shard& s = ctx->sh[i];
         if (s.natoms == 0) continue;
         CK(cudaSetDevice(s.dev));
-        int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k6_helfand_refine, K5_THREADS, smem));
-        if (occ < 1) return fail(ctx, TA_ERR_UNSUPPORTED, "K6 does not fit on an SM");
-        const int grid = (int)std::min<int64_t>(s.natoms, (int64_t)s.num_sms * occ);
-        grids[i] = grid;
-        if ((rc = ensure_partial(ctx, s, (size_t)grid))) return rc;    // drops K1's partial rows (sums of the ACF)
+        if (nflag[i] == 0) continue;                                  // nothing to correct on this shard
+        const int grid = grids[i];
         HelfandFftArgs a;
         a.series = s.series; a.by_particle = s.by_particle; a.partial = s.partial;
         a.natoms = (int)s.natoms; a.D = ctx->D; a.T = (int)ctx->T; a.Tld = ctx->Tld; a.denom = denom;
