@@ -12,6 +12,8 @@ boundary -- it contains no part of the hot path.
 """
 from __future__ import annotations
 
+import math
+
 import numpy as np
 
 try:  # pragma: no cover - exercised only where MDAnalysis is installed
@@ -107,8 +109,10 @@ except ImportError:
         a, b, c, al, be, ga = (float(v) for v in dimensions)
         if a == 0 or b == 0 or c == 0:
             return 0.0
-        ca, cb, cg = (np.cos(np.deg2rad(v)) for v in (al, be, ga))
-        return float(a * b * c * np.sqrt(max(0.0, 1 - ca * ca - cb * cb - cg * cg + 2 * ca * cb * cg)))
+        if al == 90.0 and be == 90.0 and ga == 90.0:
+            return a * b * c
+        ca, cb, cg = (math.cos(math.radians(v)) for v in (al, be, ga))
+        return a * b * c * math.sqrt(max(0.0, 1 - ca * ca - cb * cb - cg * cg + 2 * ca * cb * cg))
 
     class Timestep:
         def __init__(self, reader, frame):

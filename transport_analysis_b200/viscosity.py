@@ -95,12 +95,13 @@ class ViscosityHelfand(AnalysisBase):
 
     def _single_frame(self):
         ts = self._ts
-        if not (ts.has_velocities and ts.has_positions and ts.volume != 0):
+        volume = ts.volume if (ts.has_velocities and ts.has_positions) else 0     # one box-volume evaluation per frame
+        if volume == 0:
             raise NoDataError(
                 "Helfand viscosity computation requires "
                 "velocities, positions, and box volume in the trajectory"
             )
-        self._volumes[self._frame_index] = ts.volume
+        self._volumes[self._frame_index] = volume
         if self._stager.bulk_done:
             return
         self._stager.add_frame(self._frame_index, self.atomgroup.velocities, self.atomgroup.positions)
