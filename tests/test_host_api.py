@@ -142,3 +142,23 @@ def test_running_viscosity_reproduces_the_demo_notebook(u):
 def test_helfand_fft_route_needs_fp64(u):
     with pytest.raises(ValueError, match="fp64"):
         VH(u.atoms, fft=True, precision="fp32")
+
+
+def test_helfand_route_argument(u):
+    """fft='auto' (default): the FFT route with exact refinement in FP64, the direct lag sums in the FP32 mode;
+    True / False force a route; anything else is refused."""
+    assert VH(u.atoms).fft is True and VH(u.atoms)._fft_auto
+    assert VH(u.atoms, precision="fp32").fft is False
+    assert VH(u.atoms, fft=False).fft is False and not VH(u.atoms, fft=False)._fft_auto
+    assert VH(u.atoms, fft=True).fft is True
+    for bad in ("yes", 2, None):
+        with pytest.raises(ValueError, match="fft must be"):
+            VH(u.atoms, fft=bad)
+
+
+def test_unsupported_error_is_a_backend_error():
+    from transport_analysis_b200 import _lib
+
+    assert issubclass(_lib.UnsupportedError, _lib.BackendError) and _lib.TA_ERR_UNSUPPORTED == -4
+    with open(os.path.join(ROOT, "include", "ta_b200.h")) as f:
+        assert "#define TA_ERR_UNSUPPORTED (-4)" in f.read()
