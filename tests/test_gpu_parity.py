@@ -247,6 +247,22 @@ def test_lazy_by_particle(rand_u):
     assert np.array_equal(lazy.particles(4, 9), eager[:, 4:9])
 
 
+def test_lazy_handle_of_an_earlier_run_goes_stale(rand_u):
+    """A per-particle result left on the GPU belongs to the device buffers of its run: once run() is called again an
+    unread handle refuses to return values (they would be the new run's), a handle that was read keeps its copy."""
+    u, _, _, _ = rand_u
+    a = VACF(u.atoms, fft=True, max_eager_bytes=0)
+    read = a.run().results.vacf_by_particle
+    kept = np.array(read)
+    unread = a.run(start=5, stop=400).results.vacf_by_particle
+    assert np.array_equal(np.asarray(read), kept) and read.shape == kept.shape
+    third = a.run().results.vacf_by_particle
+    with pytest.raises(RuntimeError, match="later run"):
+        np.asarray(unread)
+    assert np.array_equal(np.asarray(third), kept)
+    assert np.array_equal(third.mean(axis=1), kept.mean(axis=1))          # ndarray methods work on the handle
+
+
 # ------------------------------------------------------------------ K1 fast path (H = 256 R1, k1_fast.cuh)
 @pytest.mark.parametrize("T,N,dim", [(1600, 5, "xyz"), (2000, 70, "xyz"), (2047, 3, "x"), (3000, 9, "yz"), (4000, 4, "xyz"),
                                      (5000, 33, "xyz"), (5001, 2, "xy"), (6000, 3, "z"), (8192, 2, "xyz"),

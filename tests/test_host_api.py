@@ -162,3 +162,43 @@ def test_unsupported_error_is_a_backend_error():
     assert issubclass(_lib.UnsupportedError, _lib.BackendError) and _lib.TA_ERR_UNSUPPORTED == -4
     with open(os.path.join(ROOT, "include", "ta_b200.h")) as f:
         assert "#define TA_ERR_UNSUPPORTED (-4)" in f.read()
+
+
+def test_lazy_by_particle_behaves_like_the_array():
+    """A per-particle result left on the GPU is fetched on first use and then acts as the (n_frames, n_particles) array the
+    reference stores: numpy functions, ndarray methods, arithmetic, indexing; particle ranges without the full fetch; a handle
+    of an earlier run that was never read refuses to return the next run's values."""
+    from transport_analysis_b200._staging import LazyByParticle
+
+    class FakeCtx:
+        def __init__(self):
+            self.data = np.arange(12.0).reshape(3, 4)      # (T, N)
+            self.fetches = []
+
+        def fetch_by_particle(self, atom0=0, natoms=None):
+            self.fetches.append((atom0, natoms))
+            return self.data[:, atom0:atom0 + natoms].copy()
+
+    ctx = FakeCtx()
+    lz = LazyByParticle(ctx, 3, 4)
+    assert lz.shape == (3, 4) and lz.ndim == 2 and len(lz) == 3 and lz.size == 12 and lz.nbytes == 96 and not ctx.fetches
+    np.testing.assert_array_equal(lz.particles(1, 3), ctx.data[:, 1:3])
+    assert ctx.fetches == [(1, 2)]
+    np.testing.assert_array_equal(lz.mean(axis=1), ctx.data.mean(axis=1))        # ndarray method -> one full fetch
+    assert ctx.fetches == [(1, 2), (0, 4)]
+    np.testing.assert_array_equal(np.mean(lz, axis=1), ctx.data.mean(axis=1))
+    np.testing.assert_array_equal(lz * 2 + 1, ctx.data * 2 + 1)
+    np.testing.assert_array_equal(1 - lz, 1 - ctx.data)
+    np.testing.assert_array_equal(lz[1:, ::2], ctx.data[1:, ::2])
+    np.testing.assert_array_equal(lz.T, ctx.data.T)
+    np.testing.assert_array_equal(lz.particles(0, 2), ctx.data[:, :2])
+    assert len(ctx.fetches) == 2                                                  # everything after the first use is cached
+    lz.invalidate()                                                               # already read: stays valid
+    np.testing.assert_array_equal(np.asarray(lz), ctx.data)
+    unread = LazyByParticle(ctx, 3, 4)
+    unread.invalidate()
+    with pytest.raises(RuntimeError, match="later run"):
+        np.asarray(unread)
+    with pytest.raises(RuntimeError, match="later run"):
+        unread.particles(0, 1)
+    assert "stale" in repr(unread) and "fetched" in repr(lz)

@@ -29,31 +29,73 @@ def resolve_devices(devices):
     return [int(d) for d in devices]
 
 
-class LazyByParticle:
-    """Array-like handle on a per-particle result that is still on the GPUs.
+class LazyByParticle(np.lib.mixins.NDArrayOperatorsMixin):
+    """Per-particle result that is still on the GPUs, behaving like the ``(n_frames, n_particles)`` float64 array
+    the reference stores (velocityautocorr.py:145-147, viscosity.py:117-119).
 
-    ``np.asarray(handle)`` or ``handle[...]`` materialises it with the
-    reference's shape ``(n_frames, n_particles)``; ``handle.particles(a, b)``
-    fetches only particles a..b-1.
+    The array is fetched the first time its values are needed -- ``np.asarray(handle)``, ``handle[...]``, arithmetic,
+    any numpy function or ndarray method / attribute (``handle.mean(axis=1)``, ``handle.T`` ...) -- and kept;
+    ``handle.particles(a, b)`` fetches only particles a..b-1 without materialising the rest.  A later ``run()`` on the
+    same analysis object overwrites the device buffer: a handle of the earlier run that was never read then refuses
+    to produce values instead of returning the new run's.
     """
 
     def __init__(self, ctx: "_lib.Context", T: int, N: int):
         self._ctx, self.shape, self.dtype, self.ndim = ctx, (T, N), np.dtype(np.float64), 2
         self._cache = None
+        self._stale = False
+
+    def _check_fresh(self):
+        if self._stale:
+            raise RuntimeError("this per-particle result was left on the GPU and a later run() has overwritten it; "
+                               "read it (np.asarray) before running again")
+
+    def invalidate(self):
+        """Called by the analysis classes when a new run() reuses the device buffers."""
+        if self._cache is None:
+            self._stale = True
 
     def particles(self, start: int, stop: int) -> np.ndarray:
+        if self._cache is not None:
+            return self._cache[:, start:stop]
+        self._check_fresh()
         return self._ctx.fetch_by_particle(start, stop - start)
 
     def __array__(self, dtype=None, copy=None):
         if self._cache is None:
+            self._check_fresh()
             self._cache = self._ctx.fetch_by_particle(0, self.shape[1])
         return self._cache if dtype is None else self._cache.astype(dtype)
+
+    def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
+        conv = lambda x: np.asarray(x) if isinstance(x, LazyByParticle) else x   # noqa: E731
+        if "out" in kwargs:
+            kwargs["out"] = tuple(conv(x) for x in kwargs["out"])
+        return getattr(ufunc, method)(*(conv(x) for x in inputs), **kwargs)
 
     def __getitem__(self, item):
         return np.asarray(self)[item]
 
     def __len__(self):
         return self.shape[0]
+
+    @property
+    def size(self):
+        return self.shape[0] * self.shape[1]
+
+    @property
+    def nbytes(self):
+        return 8 * self.size
+
+    def __getattr__(self, name):
+        # only reached for names this class does not define: ndarray methods and attributes of the fetched array
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(np.asarray(self), name)
+
+    def __repr__(self):
+        state = "fetched" if self._cache is not None else ("stale" if self._stale else "on device")
+        return f"<LazyByParticle shape={self.shape} float64, {state}>"
 
 
 class FrameStager:

@@ -16,7 +16,7 @@ Extra keyword arguments (all default to the reference's behaviour):
 ``devices``    CUDA device ids the particles are sharded over (default ``[0]``
                or ``$TA_B200_DEVICES``).
 ``max_eager_bytes``  per-particle results larger than this stay on the GPUs
-               behind a lazy array-like handle (default 1 GiB).
+               behind a lazy handle that behaves like the array and is fetched on first use (default 64 MiB).
 """
 from __future__ import annotations
 
@@ -66,7 +66,7 @@ class VelocityAutocorr(AnalysisBase):
     """
 
     def __init__(self, atomgroup, dim_type="xyz", fft=True, precision="fp64", devices=None,
-                 max_eager_bytes=1 << 30, **kwargs):
+                 max_eager_bytes=1 << 26, **kwargs):
         super().__init__(atomgroup.universe.trajectory, **kwargs)
 
         if isinstance(atomgroup, UpdatingAtomGroup):
@@ -92,6 +92,9 @@ class VelocityAutocorr(AnalysisBase):
     def _prepare(self):
         if self.n_frames < 1 or self.n_particles < 1:
             raise ValueError("VACF needs at least one frame and one particle")
+        prev = self.results.get("vacf_by_particle") if hasattr(self.results, "get") else None
+        if isinstance(prev, LazyByParticle):
+            prev.invalidate()             # the device buffers are about to be reused
         self._stager = FrameStager(self._ctx or self._devices, self.n_frames, self.n_particles, self._dim, 1, None,
                                    self.precision)
         self._stager.try_bulk(self._trajectory, self.atomgroup.ix, getattr(self, "start", None),

@@ -47,7 +47,7 @@ class ViscosityHelfand(AnalysisBase):
     """
 
     def __init__(self, atomgroup, temp_avg=300.0, dim_type="xyz", linear_fit_window=None,
-                 precision="fp64", devices=None, max_eager_bytes=1 << 30, fft="auto", **kwargs):
+                 precision="fp64", devices=None, max_eager_bytes=1 << 26, fft="auto", **kwargs):
         super().__init__(atomgroup.universe.trajectory, **kwargs)
 
         if isinstance(atomgroup, UpdatingAtomGroup):
@@ -78,6 +78,9 @@ class ViscosityHelfand(AnalysisBase):
     def _prepare(self):
         if self.n_frames < 1 or self.n_particles < 1:
             raise ValueError("viscosity computation needs at least one frame and one particle")
+        prev = self.results.get("visc_by_particle") if hasattr(self.results, "get") else None
+        if isinstance(prev, LazyByParticle):
+            prev.invalidate()             # the device buffers are about to be reused
         self._volumes = np.zeros(self.n_frames)
         self._masses = np.asarray(self.atomgroup.masses, dtype=np.float64)
         # MDAnalysis < 2.6 spells the key with a typo (reference :137-142)
