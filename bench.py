@@ -80,7 +80,7 @@ def flops_per_af(workload, T, D=3):
 
 # ---------------------------------------------------------------- helpers
 class ClockSampler:
-    """Samples SM clock and throttle reasons with nvidia-smi during the timed region."""
+    """Samples SM clock, power and throttle reasons during the timed region (NVML, else nvidia-smi)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -89,9 +89,36 @@ class ClockSampler:
     def __init__(self, device_index):
         self.dev, self.samples, self._stop, self._th = device_index, [], threading.Event(), None
 
+    # NVML clock-event reason bits (nvml.h nvmlClocksEventReason*)
+    REASON_BITS = (("sw_power_cap", 0x4), ("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
+
+    def _sample_nvml(self, nv, h):
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+        get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = int(get(h))
+        flags = {name: ("Active" if bits & bit else "Not Active") for name, bit in self.REASON_BITS}
+        return [str(sm), str(mx), f"{pw:.2f}", flags["hw_slowdown"], flags["hw_thermal_slowdown"],
+                flags["sw_thermal_slowdown"], flags["sw_power_cap"]]
+
     def _run(self):
+        # NVML in-process (a sample every 10 ms: the timed region of the default run lasts a quarter of a second);
+        # nvidia-smi as a subprocess (one sample takes ~0.1 s) when NVML is not importable
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.dev)
+            self._sample_nvml(nv, h)
+        except Exception:
+            nv = None
         while not self._stop.is_set():
             try:
+                if nv is not None:
+                    self.samples.append(self._sample_nvml(nv, h))
+                    self._stop.wait(0.01)
+                    continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.dev), f"--query-gpu={self.Q}",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 parts = [p.strip() for p in out.strip().split(",")]
