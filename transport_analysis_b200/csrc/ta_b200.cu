@@ -1272,12 +1272,13 @@ int ta_helfand_fft(ta_ctx* ctx, const double* volumes, double boltzmann, double 
         CK(cudaMemcpyAsync(&nflag[i], counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.s_compute));
     }
     bool need_k3 = false;
+    ctx->helfand_fft_flagged = 0;
     for (size_t i = 0; i < ctx->sh.size(); ++i) {
         Shard& s = ctx->sh[i];
         if (s.natoms == 0) continue;
         CK(cudaSetDevice(s.dev));
         CK(cudaStreamSynchronize(s.s_compute));
-        ctx->helfand_fft_flagged = (i == 0 ? 0 : ctx->helfand_fft_flagged) + (long long)nflag[i];
+        ctx->helfand_fft_flagged += (long long)nflag[i];
         if ((double)nflag[i] > 0.02 * (double)s.natoms * (double)ctx->T) need_k3 = true;
     }
     if (need_k3) {
