@@ -715,10 +715,12 @@ int launch_fft_r8(ta_ctx* ctx, std::vector<int>* grids) {
 }
 
 // k1_fast.cuh VAR bits served per R1: 0 and 4 (bulk series prefetch) everywhere, the other experiments at R1 = 20.
-// Default: prefetch on (measured 25.4 -> 24.2 ms at 100k x 10k); TA_B200_K1F_VAR overrides.
+// Default: prefetch on where its buffer does not cost a resident CTA (R1 >= 8; measured 25.4 -> 24.2 ms at 100k x 10k,
+// 25.1 -> 23.6 ms at 200k x 5k), off at R1 = 4 and 6 (six -> five and four -> three CTAs per SM: 6.15 -> 6.21 ms at
+// 150k x 2,000, 6.41 -> 6.87 ms at 100k x 3,000); TA_B200_K1F_VAR overrides.
 template <int R1>
 int launch_fft_fast_var(ta_ctx* ctx, std::vector<int>* grids) {
-    const int var = env_int("TA_B200_K1F_VAR", K1F_VAR_PREFETCH);
+    const int var = env_int("TA_B200_K1F_VAR", R1 >= 8 ? K1F_VAR_PREFETCH : 0);
     constexpr int NT = k1f_threads(R1);
     if (var == 0) return launch_fft_fast_r1<R1, NT, false, 0>(ctx, grids);
     if (var == 4) {
