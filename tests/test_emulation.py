@@ -215,3 +215,35 @@ def test_fast_fft_kernel_variants(emu, T, R1, var):
     for a in range(N):
         assert_close_normwise(bp[a, :T], oracle.tidynamics_acf(x[:, a, :]), 1e-12, f"T={T} atom {a}")
     np.testing.assert_allclose(part.sum(axis=0)[:T], bp.sum(axis=0)[:T], rtol=1e-13, atol=1e-13)
+
+
+# ------------------------------------------------------------------ boundary lengths of every fast-path instantiation
+def _boundary_lengths(step, radices, lo_ok):
+    """For H = step * R: the longest T (= 2H), the odd one below it, and the shortest T the selection rule sends to R."""
+    out = []
+    for R in radices:
+        H = step * R
+        out += [(2 * H, R), (2 * H - 1, R)]
+        t_min = max(lo_ok, 2 * ((3 * H - 3 + 3) // 4) - 1)      # 3 H <= 4 nh + 3  ->  nh >= (3 H - 3) / 4
+        out.append((t_min + 2, R))
+    return out
+
+
+@pytest.mark.parametrize("T,R1", _boundary_lengths(256, [4, 6, 8, 10, 12, 16, 20], 1535))
+def test_three_pass_kernel_at_the_ends_of_every_length_range(emu, T, R1):
+    if emu.emu_k1fast_r1(T) != R1:
+        pytest.skip(f"T={T} is served by R1={emu.emu_k1fast_r1(T)}")
+    x = np.random.default_rng(T).standard_normal((T, 1, 2))
+    bp, part = emu_fast(emu, x, 1, R1)
+    assert_close_normwise(bp[0], oracle.tidynamics_acf(x[:, 0, :]), 1e-12, f"T={T} R1={R1}")
+    np.testing.assert_array_equal(part[0], bp[0])
+
+
+@pytest.mark.parametrize("T,R", _boundary_lengths(512, [4, 5, 6, 8, 10, 12], 3071))
+def test_radix8_kernel_at_the_ends_of_every_length_range(emu, T, R):
+    if emu.emu_k1r8_r(T) != R:
+        pytest.skip(f"T={T} is served by R={emu.emu_k1r8_r(T)}")
+    x = np.random.default_rng(T).standard_normal((T, 1, 2))
+    bp, part = emu_r8(emu, x, 1, R)
+    assert_close_normwise(bp[0], oracle.tidynamics_acf(x[:, 0, :]), 1e-12, f"T={T} R={R}")
+    np.testing.assert_allclose(part[0], bp[0], rtol=0, atol=0)
