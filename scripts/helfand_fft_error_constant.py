@@ -11,15 +11,18 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from test_gpu_parity import BOX, VH, _helfand_case, make_universe  # noqa: E402
 
-os.environ["TA_B200_HELFAND_FFT_THR"] = "0"          # nothing is refined
+os.environ["TA_B200_HELFAND_FFT_THR"] = "-1"         # floor = -sum g^2: nothing is refined (read by ta_helfand_fft only)
 eps = 2.0 ** -53
 for kind, T, N in [("white", 3000, 40), ("smooth", 3000, 40), ("walk", 5000, 60), ("ramp", 2000, 3), ("white", 10000, 40),
-                   ("smooth", 10000, 20), ("walk", 12000, 20)]:
-    vel, pos = _helfand_case(kind, T, N, seed=T + N)
-    masses = np.random.default_rng(1).choice([1.008, 12.011, 15.999], N)
+                   ("smooth", 10000, 20), ("walk", 12000, 20), ("spike1", 3000, 40), ("offset_above", 3000, 24),
+                   ("offset_below", 3000, 24), ("piecewise", 3000, 16), ("masses200", 5000, 64), ("white", 28999, 3),
+                   ("smooth", 28999, 3)]:
+    vel, pos, masses = _helfand_case(kind, T, N, seed=T + N)
     u = make_universe(pos, vel, masses=masses, dimensions=BOX)
-    exact = VH(u.atoms).run()
-    fast = VH(u.atoms, fft=True).run()
+    exact = VH(u.atoms, fft=False).run()            # the direct sums (K3): the comparator
+    fast = VH(u.atoms, fft=True).run()              # S1 - 2 S2, un-refined
+    assert exact.fft is False and fast.fft is True
+    assert fast._ctx.helfand_fft_refined() == 0, fast._ctx.helfand_fft_refined()
     scale = 2 * exact.boltzmann * exact._vol_avg * exact.temp_avg * 3            # denom * D
     e, f = np.asarray(exact.results.visc_by_particle), np.asarray(fast.results.visc_by_particle)
     nk = (T - np.arange(T))[:, None]

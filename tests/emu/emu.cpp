@@ -11,13 +11,18 @@
 #include "../../transport_analysis_b200/csrc/fft_core.cuh"
 #include "../../transport_analysis_b200/csrc/windowed_core.cuh"
 #include "../../transport_analysis_b200/csrc/k1_fast.cuh"
-#include "../../transport_analysis_b200/csrc/k1_r8.cuh"
 #include "fiber_cta.h"
 
 using namespace ta;
 
+// the series as the kernels find them in HBM: stored in the arithmetic type R
 template <typename R>
-static int run_fft(const double* series, int T, int D, int Tld, int nthr, double* row, double* partial) {
+static std::vector<R> series_as(const double* series, size_t n) { return std::vector<R>(series, series + n); }
+
+template <typename R>
+static int run_fft(const double* series_f64, int T, int D, int Tld, int nthr, double* row, double* partial) {
+    const std::vector<R> series_r = series_as<R>(series_f64, (size_t)D * Tld);
+    const R* series = series_r.data();
     FftPlanHost hp;
     int rc = ta_build_fft_plan(T, &hp);
     if (rc) return rc;
@@ -59,7 +64,9 @@ static int run_fft(const double* series, int T, int D, int Tld, int nthr, double
 }
 
 template <typename R>
-static int run_win(const double* series, int T, int D, int Tld, int mode, int nwarps, double* res) {
+static int run_win(const double* series_f64, int T, int D, int Tld, int mode, int nwarps, double* res) {
+    const std::vector<R> series_r = series_as<R>(series_f64, (size_t)D * Tld);
+    const R* series = series_r.data();
     // the kernel body itself (windowed_core.cuh win_body) for one particle, one CTA of nwarps warps;
     // returns the un-normalised lag sums (row * (T - k) [* D * denom])
     const int ne = win_smem_elems(T);
@@ -80,102 +87,53 @@ static int run_win(const double* series, int T, int D, int Tld, int mode, int nw
     return 0;
 }
 
-template <int R1, int VAR = 0>
-static int run_k1fast(const double* series, int T, int D, int Tld, int natoms, int nblk, double* by_particle,
+template <int R1, typename RT>
+static int run_k1fast(const double* series_f64, int T, int D, int Tld, int natoms, int nblk, double* by_particle,
                       double* partial) {
     K1FastPlan p;
     int rc = k1f_build_plan(T, Tld, R1, &p);
     if (rc) return rc;
-    K1FArgs a;
-    a.series = series; a.by_particle = by_particle; a.partial = partial;
-    a.omega = reinterpret_cast<const cd*>(p.omega.data());
-    a.tw2 = reinterpret_cast<const cd*>(p.tw2.data());
-    a.tw8 = reinterpret_cast<const cd*>(p.tw8.data());
+    const std::vector<RT> series = series_as<RT>(series_f64, (size_t)natoms * D * Tld);
+    const std::vector<RT> omega(p.omega.begin(), p.omega.end()), tw2(p.tw2.begin(), p.tw2.end()),
+        wbase(p.wbase.begin(), p.wbase.end()), inv(p.inv.begin(), p.inv.end());
+    K1FArgs<RT> a;
+    a.series = series.data(); a.by_particle = by_particle; a.partial = partial;
+    a.omega = reinterpret_cast<const cplx<RT>*>(omega.data());
+    a.tw2 = reinterpret_cast<const cplx<RT>*>(tw2.data());
     a.map = p.map.data();
-    a.wbase = reinterpret_cast<const cd*>(p.wbase.data());
-    a.inv = p.inv.data();
-    a.natoms = natoms; a.D = D; a.T = T; a.nh = p.nh; a.Tld = Tld; a.prefetch = 0; a.stagger = 0; a.prof = nullptr;
-    std::vector<unsigned char> smem(k1f_smem_bytes(R1, VAR) + 64);
+    a.wbase = reinterpret_cast<const cplx<RT>*>(wbase.data());
+    a.inv = inv.data();
+    a.natoms = natoms; a.D = D; a.T = T; a.nh = p.nh; a.Tld = Tld;
+    constexpr bool PREF = k1f_prefetch(R1, (int)sizeof(RT));        // the build the library ships for this (R1, RT)
+    std::vector<unsigned char> smem(k1f_smem_bytes(R1, PREF, (int)sizeof(RT)) + 64);
     unsigned char* sm = smem.data() + (16 - ((uintptr_t)smem.data() & 15)) % 16;
     for (int bid = 0; bid < nblk; ++bid)
-        emu::run_cta(k1f_threads(R1), [&](int tid) { k1f_body<R1, k1f_threads(R1), emu::EmuCtx, false, VAR>(a, sm, tid, bid, nblk); });
+        emu::run_cta(k1f_threads(R1), [&](int tid) { k1f_body<R1, k1f_threads(R1), emu::EmuCtx, RT, PREF>(a, sm, tid, bid, nblk); });
     return 0;
 }
 
-template <int R>
-static int run_k1r8(const double* series, int T, int D, int Tld, int natoms, int nblk, double* by_particle, double* partial) {
-    K1R8Plan p;
-    int rc = k1e_build_plan(T, R, &p);
-    if (rc) return rc;
-    K1EArgs a;
-    a.series = series; a.by_particle = by_particle; a.partial = partial;
-    a.omega = reinterpret_cast<const cd*>(p.omega.data());
-    a.tw2 = reinterpret_cast<const cd*>(p.tw2.data());
-    a.tw3 = reinterpret_cast<const cd*>(p.tw3.data());
-    a.map = p.map.data();
-    a.wbase = reinterpret_cast<const cd*>(p.wbase.data());
-    a.natoms = natoms; a.D = D; a.T = T; a.nh = p.nh; a.Tld = Tld; a.sm_slots = nullptr; a.stagger = 0;
-    std::vector<unsigned char> smem(k1e_smem_bytes(R) + 64);
-    unsigned char* sm = smem.data() + (16 - ((uintptr_t)smem.data() & 15)) % 16;
-    for (int bid = 0; bid < nblk; ++bid)
-        emu::run_cta(k1e_threads(R), [&](int tid) { k1e_body<R, emu::EmuCtx>(a, sm, tid, bid, nblk); });
-    return 0;
+template <typename RT>
+static int run_k1fast_any(const double* series, int T, int D, int Tld, int natoms, int nblk, int R1, double* by_particle, double* partial) {
+    switch (R1) {
+        case 4: return run_k1fast<4, RT>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 6: return run_k1fast<6, RT>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 8: return run_k1fast<8, RT>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 10: return run_k1fast<10, RT>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 12: return run_k1fast<12, RT>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 16: return run_k1fast<16, RT>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 20: return run_k1fast<20, RT>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 24: return run_k1fast<24, RT>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+    }
+    return -1;
 }
 
 extern "C" {
-int emu_k1r8_r(int T) { return k1e_choose_r(T); }
-int emu_k1r8(const double* series, int T, int D, int Tld, int natoms, int nblk, int R, double* by_particle, double* partial) {
-    switch (R) {
-        case 4: return run_k1r8<4>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-        case 5: return run_k1r8<5>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-        case 6: return run_k1r8<6>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-        case 8: return run_k1r8<8>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-        case 10: return run_k1r8<10>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-        case 12: return run_k1r8<12>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-    }
-    return -1;
-}
-// the plan's thread maps, for structural checks: returns NT, fills map[2 * NT]
-int emu_k1r8_map(int T, int R, unsigned* map) {
-    K1R8Plan p;
-    int rc = k1e_build_plan(T, R, &p);
-    if (rc) return rc;
-    for (size_t i = 0; i < p.map.size(); ++i) map[i] = p.map[i];
-    return p.NT;
-}
 int emu_k1fast_r1(int T) { return k1f_choose_r1(T); }
-// the experiment variants of the three-pass kernel (k1_fast.cuh VAR bits) at R1 = 20 and R1 = 10
-int emu_k1fast_var(const double* series, int T, int D, int Tld, int natoms, int nblk, int R1, int var, double* by_particle,
-                   double* partial) {
-    if (R1 == 20) switch (var) {
-        case 1: return run_k1fast<20, 1>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-        case 2: return run_k1fast<20, 2>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-        case 4: return run_k1fast<20, 4>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-        case 6: return run_k1fast<20, 6>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-        case 8: return run_k1fast<20, 8>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-        case 12: return run_k1fast<20, 12>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-        case 52: return run_k1fast<20, 52>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-    }
-    if (R1 == 10) switch (var) {
-        case 12: return run_k1fast<10, 12>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-        case 2: return run_k1fast<10, 2>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-        case 4: return run_k1fast<10, 4>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-        case 6: return run_k1fast<10, 6>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-    }
-    return -1;
-}
-int emu_k1fast(const double* series, int T, int D, int Tld, int natoms, int nblk, int R1, double* by_particle,
+// the three-pass kernel body as shipped for (R1, precision): use_f32 = 0 FP64, 1 FP32 (float series, float arithmetic)
+int emu_k1fast(const double* series, int T, int D, int Tld, int natoms, int nblk, int R1, int use_f32, double* by_particle,
                double* partial) {
-    switch (R1) {
-        case 4: return run_k1fast<4>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-        case 6: return run_k1fast<6>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-        case 8: return run_k1fast<8>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-        case 10: return run_k1fast<10>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-        case 12: return run_k1fast<12>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-        case 16: return run_k1fast<16>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-        case 20: return run_k1fast<20>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-    }
-    return -1;
+    return use_f32 ? run_k1fast_any<float>(series, T, D, Tld, natoms, nblk, R1, by_particle, partial)
+                   : run_k1fast_any<double>(series, T, D, Tld, natoms, nblk, R1, by_particle, partial);
 }
 int emu_fft_acf(const double* series, int T, int D, int Tld, int nthr, int use_f32, double* row, double* partial) {
     return use_f32 ? run_fft<float>(series, T, D, Tld, nthr, row, partial)

@@ -140,32 +140,16 @@ struct EmuCtx {
     static void sync_warp() { emu::sync_warp(); }
     static double shfl_xor16(double v) { return emu::shfl_xor(v, 16); }
     static double shfl_xor(double v, int mask) { return emu::shfl_xor(v, mask); }
-    static void prefetch_l2(const void*, size_t, int, int) {}
-    static long long clock() { return 0; }
-    static void spin(int) {}
-    static void stagger_second_cta(unsigned*, int, int) {}
-    static long long clock_after(double) { return 0; }
     static void compiler_fence() {}
-    // named barriers count threads here (the hardware counts threads too, a warp at a time)
-    static void bar_sync(int id, int count) { emu::named_sync(id, count); }
-    static void bar_arrive(int id, int count) { emu::named_arrive(id, count); }
-    static double rcp(double a) { return 1.0 / a; }
-    static void fence_async_smem() {}
     // mbarrier with one arrival per phase: *bar counts completed phases; a wait on parity P returns once the
     // phase of that parity is over (the hardware's try_wait.parity); the bulk load completes when it is issued
     static void mbar_init(unsigned long long* bar) { *bar = 0; }
     static void mbar_wait(unsigned long long* bar, unsigned parity) {
         while ((*bar & 1ull) == (unsigned long long)parity) emu::yield_now();
     }
-    template <class V> static void bulk_load(V* dst, const double* src, unsigned bytes, unsigned long long* bar) {
+    static void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
         memcpy(dst, src, bytes);
         ++*bar;
-    }
-    static void bulk_wait_all() {}
-    // the bulk-copy engine, done at once: every writer has arrived at the hand-over barrier before the issue
-    template <class V> static void bulk_store_and_add(V* row, V* part, const V* src, unsigned bytes) {
-        const unsigned n = bytes / sizeof(V);
-        for (unsigned i = 0; i < n; ++i) { row[i] = src[i]; part[i].x += src[i].x; part[i].y += src[i].y; }
     }
     template <class V> static V ld_stream(const V* p) { return *p; }
 };

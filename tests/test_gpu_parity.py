@@ -177,19 +177,6 @@ def test_notebook_helfand_t10(route):
     assert_allclose(VH(u.atoms, fft=route).run().results.timeseries * 3, oracle.NOTEBOOK_HELFAND_T10_SUMDIMS, rtol=1e-10)
 
 
-def test_helfand_default_route_falls_back_to_the_direct_sums_beyond_its_length():
-    """fft='auto' on a trajectory longer than the FFT route's finishing kernel holds (T > ~29,000): the direct kernel."""
-    T, N = 30001, 2
-    vel, pos = random_trajectory(T, N, seed=3, with_positions=True, rho=0.9)
-    u = make_universe(pos, vel, masses=[12.0, 16.0], dimensions=BOX)
-    h = VH(u.atoms).run()
-    assert h.fft is False
-    lags = [1, 2, 15000, 30000]
-    ref_bp, _ = oracle.helfand_msd(_f64(vel), _f64(pos), np.array([12.0, 16.0]),
-                                   np.full(T, float(np.prod(np.float32(BOX[:3]).astype(np.float64)))), 300.0, lags=lags)
-    assert_allclose(np.asarray(h.results.visc_by_particle)[lags], ref_bp[lags], rtol=TOL64)
-
-
 # ------------------------------------------------------------------ C ABI direct
 def test_c_abi_f64_source_lag_major_and_errors():
     rng = np.random.default_rng(21)
@@ -229,13 +216,20 @@ def test_results_are_bit_reproducible(rand_u):
     assert np.array_equal(a, b)
 
 
-def test_fp32_mode(rand_u):
+def test_fp32_mode(rand_u, monkeypatch):
     u, vel, pos, masses = rand_u
     for fft in (True, False):
         ref_bp, ref_ts = (oracle.vacf_fft if fft else oracle.vacf_windowed)(_f64(vel))
         v = VACF(u.atoms, fft=fft, precision="fp32").run()
         assert_close_normwise(v.results.timeseries, ref_ts, TOL32)
         assert_close_normwise(v.results.vacf_by_particle, ref_bp, TOL32)
+    # one context, FP64 then FP32 then FP64: the series buffers are rebuilt in the arithmetic type
+    a = VACF(u.atoms, fft=True)
+    first = np.array(a.run().results.timeseries)
+    a.precision = "fp32"
+    assert_close_normwise(a.run().results.timeseries, first, TOL32)
+    a.precision = "fp64"
+    assert np.array_equal(a.run().results.timeseries, first)
 
 
 def test_lazy_by_particle(rand_u):
@@ -265,91 +259,49 @@ def test_lazy_handle_of_an_earlier_run_goes_stale(rand_u):
 
 # ------------------------------------------------------------------ K1 fast path (H = 256 R1, k1_fast.cuh)
 @pytest.mark.parametrize("T,N,dim", [(1600, 5, "xyz"), (2000, 70, "xyz"), (2047, 3, "x"), (3000, 9, "yz"), (4000, 4, "xyz"),
-                                     (5000, 33, "xyz"), (5001, 2, "xy"), (6000, 3, "z"), (8192, 2, "xyz"),
-                                     (10000, 5, "xyz"), (10240, 1, "xyz")])
+                                     (5000, 333, "xyz"), (5001, 2, "xy"), (6000, 3, "z"), (8192, 2, "xyz"),
+                                     (10000, 301, "xyz"), (10240, 1, "xyz"), (10241, 3, "xz"), (12000, 150, "xyz"),
+                                     (12288, 2, "y")])
 def test_fft_fast_path_vs_oracle_and_general_kernel(T, N, dim, monkeypatch):
-    """Every R1 instantiation of the three-pass kernel: against the oracle, and
-    against the general mixed-radix kernel (TA_B200_FFT_GENERAL=1) on the same data."""
-    monkeypatch.setenv("TA_B200_K1_PATH", "r16")
+    """Every R1 instantiation of the three-pass kernel (4 ... 24): against the oracle, and against the general
+    mixed-radix kernel (TA_B200_K1_PATH=general, read when a context is created) on the same data.
+    N > 148 makes CTAs take several particles (prefetch-buffer hand-over across particles)."""
     vel, _ = random_trajectory(T, N, seed=T + N, rho=0.8)
     u = make_universe(None, vel)
     cols, _ = oracle.parse_dim_type(dim)
     v = VACF(u.atoms, dim_type=dim, fft=True).run()
     plan = v._ctx.fft_plan_info()
     assert plan["radices"][1:] == [16, 16] and plan["H"] == 256 * plan["radices"][0], plan
-    ref_bp, ref_ts = oracle.vacf_fft(_f64(vel)[:, :, cols])
-    assert_close_normwise(v.results.vacf_by_particle, ref_bp, TOL64, "fast vs oracle, by particle")
-    assert_close_normwise(v.results.timeseries, ref_ts, TOL64, "fast vs oracle, timeseries")
-    monkeypatch.setenv("TA_B200_FFT_GENERAL", "1")
-    g = VACF(u.atoms, dim_type=dim, fft=True).run()
-    assert g._ctx.fft_plan_info()["radices"][1:] != [16, 16]
-    assert_close_normwise(g.results.vacf_by_particle, v.results.vacf_by_particle, 1e-11, "fast vs general kernel")
-
-
-# ------------------------------------------------------------------ K1 radix-8 path (H = 512 R, k1_r8.cuh)
-@pytest.mark.parametrize("T,N,dim", [(3100, 5, "xyz"), (4000, 70, "xyz"), (4096, 3, "x"), (5000, 333, "xyz"), (5001, 2, "xy"),
-                                     (6000, 9, "yz"), (7000, 3, "z"), (8192, 2, "xyz"), (9999, 4, "xz"),
-                                     (10000, 301, "xyz"), (10240, 1, "xyz"), (12000, 5, "xyz")])
-def test_fft_radix8_path_vs_oracle_and_other_kernels(T, N, dim, monkeypatch):
-    """Every R instantiation of the four-pass radix-8 kernel: against the oracle, against the general mixed-radix
-    kernel and, where it has an instantiation, the three-pass radix-16 kernel.
-    N > 148 makes CTAs take several particles (staging-buffer hand-over, bulk reduce into the partial row)."""
-    monkeypatch.setenv("TA_B200_K1_PATH", "r8")
-    vel, _ = random_trajectory(T, N, seed=T + N, rho=0.8)
-    u = make_universe(None, vel)
-    cols, _ = oracle.parse_dim_type(dim)
-    v = VACF(u.atoms, dim_type=dim, fft=True).run()
-    plan = v._ctx.fft_plan_info()
-    assert plan["radices"][1:] == [8, 8, 8] and plan["H"] == 512 * plan["radices"][0], plan
     n_or = min(N, 6)                                   # the oracle is a Python loop over particles
     ref_bp, _ = oracle.vacf_fft(_f64(vel)[:, :n_or, cols])
-    assert_close_normwise(v.results.vacf_by_particle[:, :n_or], ref_bp, TOL64, "radix-8 vs oracle, by particle")
+    assert_close_normwise(v.results.vacf_by_particle[:, :n_or], ref_bp, TOL64, "fast vs oracle, by particle")
     assert_close_normwise(v.results.timeseries, v.results.vacf_by_particle.mean(axis=1), 1e-13, "timeseries = particle mean")
     again = VACF(u.atoms, dim_type=dim, fft=True).run()
     assert np.array_equal(again.results.timeseries, v.results.timeseries)          # bit-reproducible
     assert np.array_equal(again.results.vacf_by_particle, v.results.vacf_by_particle)
-    for path in ("general", "r16"):
-        monkeypatch.setenv("TA_B200_K1_PATH", path)
-        g = VACF(u.atoms, dim_type=dim, fft=True).run()
-        if path == "r16" and g._ctx.fft_plan_info()["radices"][1:] != [16, 16]:
-            continue
-        assert g._ctx.fft_plan_info()["smem_bytes"] != plan["smem_bytes"]        # a different kernel served the call
-        assert_close_normwise(g.results.vacf_by_particle, v.results.vacf_by_particle, 1e-11, f"radix-8 vs {path}")
-        assert_close_normwise(g.results.timeseries, v.results.timeseries, 1e-11, f"radix-8 vs {path}, timeseries")
+    monkeypatch.setenv("TA_B200_K1_PATH", "general")
+    g = VACF(u.atoms, dim_type=dim, fft=True).run()
+    assert g._ctx.fft_plan_info()["radices"][1:] != [16, 16]
+    assert_close_normwise(g.results.vacf_by_particle, v.results.vacf_by_particle, 1e-11, "fast vs general kernel")
+    assert_close_normwise(g.results.timeseries, v.results.timeseries, 1e-11, "fast vs general kernel, timeseries")
 
 
 @pytest.mark.parametrize("T,want", [(1000, None), (2000, [4, 16, 16]), (5000, [10, 16, 16]), (10000, [20, 16, 16]),
-                                    (12000, [12, 8, 8, 8]), (13000, None)])
+                                    (12000, [24, 16, 16]), (13000, None)])
 def test_fft_default_kernel_choice(T, want):
-    """Three-pass radix-16 path where it has an instantiation, radix-8 path above it (T <= 12,288), else the general kernel."""
+    """Three-pass radix-16 kernel where it has an instantiation (T <= 12,288), else the general kernel; both precisions."""
     vel, _ = random_trajectory(T, 2, seed=T, rho=0.5)
-    v = VACF(make_universe(None, vel).atoms, fft=True).run()
-    rad = v._ctx.fft_plan_info()["radices"]
-    if want is None:
-        assert not (len(rad) == 3 and rad[1:] == [16, 16]) and not (len(rad) == 4 and rad[1:] == [8, 8, 8]), rad
-    else:
-        assert rad == want, rad
     ref_bp, ref_ts = oracle.vacf_fft(_f64(vel))
-    assert_close_normwise(v.results.vacf_by_particle, ref_bp, TOL64, f"T={T}")
-    assert_close_normwise(v.results.timeseries, ref_ts, TOL64, f"T={T}")
-
-
-@pytest.mark.parametrize("var", [0, 1, 2, 3, 4, 5, 8, 12])
-def test_fft_three_pass_kernel_variants(var, monkeypatch):
-    """k1_fast.cuh VAR bits at R1 = 20 (token-ordered loads, staged bulk output, bulk series prefetch = the default):
-    same results whichever way the data moves.  N > 148 makes CTAs take several particles."""
-    T, N = 10000, 301
-    vel, _ = random_trajectory(T, N, seed=var, rho=0.7)
-    u = make_universe(None, vel)
-    monkeypatch.setenv("TA_B200_K1F_VAR", str(var))
-    v = VACF(u.atoms, fft=True).run()
-    assert v._ctx.fft_plan_info()["radices"] == [20, 16, 16]
-    ref_bp, _ = oracle.vacf_fft(_f64(vel)[:, :4])
-    assert_close_normwise(v.results.vacf_by_particle[:, :4], ref_bp, TOL64, f"variant {var} vs oracle")
-    assert_close_normwise(v.results.timeseries, v.results.vacf_by_particle.mean(axis=1), 1e-13, "timeseries = particle mean")
-    again = VACF(u.atoms, fft=True).run()
-    assert np.array_equal(again.results.timeseries, v.results.timeseries)
-    assert np.array_equal(again.results.vacf_by_particle, v.results.vacf_by_particle)
+    for precision, tol in (("fp64", TOL64), ("fp32", TOL32)):
+        v = VACF(make_universe(None, vel).atoms, fft=True, precision=precision).run()
+        rad = v._ctx.fft_plan_info()["radices"]
+        if want is None:
+            assert not (len(rad) == 3 and rad[1:] == [16, 16]), rad
+        else:
+            assert rad == want, rad
+        cut = None if precision == "fp64" else -8          # FP32: lags with at least 8 origins (DESIGN.md "FP32 mode")
+        assert_close_normwise(v.results.vacf_by_particle[:cut], ref_bp[:cut], tol, f"T={T} {precision}")
+        assert_close_normwise(v.results.timeseries[:cut], ref_ts[:cut], tol, f"T={T} {precision}")
 
 
 @pytest.mark.parametrize("T,N,dim", [(19000, 3, "xyz"), (20001, 150, "xyz"), (30000, 2, "y"), (65536, 2, "xz")])
@@ -371,9 +323,8 @@ def test_fft_route_beyond_shared_memory(T, N, dim):
         assert_close_normwise(v.results.timeseries, ref_ts, TOL64, f"T={T} timeseries")
 
 
-def test_fft_fast_path_ramp_known_answer(monkeypatch):
+def test_fft_fast_path_ramp_known_answer():
     """The reference's step trajectory (v = t, 5001 frames) takes the fast path (R1 = 10)."""
-    monkeypatch.setenv("TA_B200_K1_PATH", "r16")
     t = np.arange(5001, dtype=np.float64)
     v = np.repeat(t[:, None, None], 3, axis=2)
     u = make_universe(None, v)
@@ -382,11 +333,6 @@ def test_fft_fast_path_ramp_known_answer(monkeypatch):
     poly = oracle.characteristic_poly(5001, 3)
     assert_almost_equal(a.results.timeseries, poly, decimal=3)     # the reference's own bar (tests :454-469)
     assert_close_normwise(a.results.timeseries, poly, TOL64)
-    monkeypatch.setenv("TA_B200_K1_PATH", "r8")
-    b = VACF(u.atoms, fft=True).run()
-    assert b._ctx.fft_plan_info()["radices"] == [5, 8, 8, 8]
-    assert_almost_equal(b.results.timeseries, poly, decimal=3)
-    assert_close_normwise(b.results.timeseries, poly, TOL64)
 
 
 # ------------------------------------------------------------------ size-independent properties at BASELINE sizes
@@ -449,7 +395,7 @@ def test_properties_at_config4_full_size():
 def test_properties_at_config2_and_config3_full_size():
     """BASELINE config 2 (windowed VACF, 1,000 x 2,000) and config 3 (Helfand, 10,000 x 5,000) at full size: sampled
     particles against the oracle, windowed == FFT route on all particles, Helfand row 0 == 0, timeseries == particle mean,
-    g -> 2 g gives 4 x the Helfand MSD, default route (FFT + exact refinement) == direct lag sums to 1e-10 everywhere."""
+    g -> 2 g gives 4 x the Helfand MSD, opt-in route (FFT + exact refinement) == default direct lag sums to 1e-10 everywhere."""
     import bench
 
     # ---- config 2
@@ -474,7 +420,7 @@ def test_properties_at_config2_and_config3_full_size():
     pos *= np.float32(10.0)
     masses = np.random.default_rng(3).choice([1.008, 12.011, 15.999], N)
     u = make_universe(pos, vel, masses=masses, dimensions=BOX)
-    h = VH(u.atoms).run()
+    h = VH(u.atoms, fft=True).run()
     bp, ts = np.asarray(h.results.visc_by_particle), h.results.timeseries
     assert ts[0] == 0.0 and np.all(bp[0] == 0.0)
     assert_allclose(ts, bp.mean(axis=1), rtol=1e-12)
@@ -487,7 +433,7 @@ def test_properties_at_config2_and_config3_full_size():
     assert h.fft is True and hd.fft is False
     assert_allclose(hd.results.timeseries, ts, rtol=TOL64)
     assert_allclose(np.asarray(hd.results.visc_by_particle), bp, rtol=TOL64)
-    h2 = VH(make_universe(pos[:, :256], vel[:, :256] * np.float32(2.0), masses=masses[:256], dimensions=BOX).atoms).run()
+    h2 = VH(make_universe(pos[:, :256], vel[:, :256] * np.float32(2.0), masses=masses[:256], dimensions=BOX).atoms, fft=True).run()
     assert_allclose(np.asarray(h2.results.visc_by_particle), 4.0 * bp[:, :256], rtol=1e-12)
 
 
@@ -501,10 +447,16 @@ def test_multi_gpu_sharding_matches_single():
     two = VACF(u.atoms, devices=list(range(min(n, 4)))).run()
     assert np.array_equal(one.results.vacf_by_particle, two.results.vacf_by_particle)
     assert_allclose(one.results.timeseries, two.results.timeseries, rtol=1e-13, atol=1e-14)
-    h1 = VH(u.atoms, devices=[0]).run()
-    h2 = VH(u.atoms, devices=[0, 1]).run()
-    assert np.array_equal(h1.results.visc_by_particle, h2.results.visc_by_particle)
-    assert_allclose(h1.results.timeseries, h2.results.timeseries, rtol=1e-13)
+    ref_bp, ref_ts = oracle.vacf_fft(_f64(vel))
+    assert_close_normwise(two.results.timeseries, ref_ts, TOL64, "NCCL-reduced timeseries vs oracle")
+    assert_close_normwise(two.results.vacf_by_particle, ref_bp, TOL64)
+    _, ref_h = oracle.helfand_msd(_f64(vel), _f64(pos), np.ones(101), np.full(400, np.prod(BOX[:3])), 300.0)
+    for route in (False, True):
+        h1 = VH(u.atoms, devices=[0], fft=route).run()
+        h2 = VH(u.atoms, devices=[0, 1], fft=route).run()
+        assert np.array_equal(h1.results.visc_by_particle, h2.results.visc_by_particle)
+        assert_allclose(h1.results.timeseries, h2.results.timeseries, rtol=1e-13)
+        assert_allclose(h2.results.timeseries, ref_h, rtol=TOL64)
 
 
 # ------------------------------------------------------------------ pipelined bulk staging (particle chunks)
@@ -516,6 +468,7 @@ def test_bulk_staging_in_particle_chunks(rand_u, chunk, monkeypatch):
     u, vel, pos, masses = rand_u
     base = VACF(u.atoms, fft=True).run()
     hbase = VH(u.atoms).run()
+    hfbase = VH(u.atoms, fft=True).run()
     wbase = VACF(u.atoms, fft=False).run()
     monkeypatch.setenv("TA_B200_BULK_CHUNK", str(chunk))
     v = VACF(u.atoms, fft=True).run()
@@ -530,6 +483,9 @@ def test_bulk_staging_in_particle_chunks(rand_u, chunk, monkeypatch):
     assert_allclose(h.results.timeseries, hbase.results.timeseries, rtol=1e-13)
     ref_bp, ref_ts = oracle.helfand_msd(_f64(vel), _f64(pos), masses, np.full(len(vel), np.prod(BOX[:3])), 300.0)
     assert_allclose(h.results.timeseries, ref_ts, rtol=TOL64)
+    hf = VH(u.atoms, fft=True).run()
+    assert np.array_equal(hf.results.visc_by_particle, hfbase.results.visc_by_particle)
+    assert_allclose(hf.results.timeseries, ref_ts, rtol=TOL64)
 
 
 def test_second_run_on_the_same_object_and_window(rand_u, monkeypatch):
@@ -549,39 +505,68 @@ def test_second_run_on_the_same_object_and_window(rand_u, monkeypatch):
     assert_allclose(a._ctx.vacf_fft(), sub.results.timeseries, rtol=1e-13, atol=1e-15)
 
 
-# ------------------------------------------------------------------ opt-in FFT route of the Helfand MSD (K1 + K5)
+# ------------------------------------------------------------------ opt-in FFT route of the Helfand MSD (K1 + K5 + K6)
+# Comparators: the DIRECT route (fft=False, kernel K3: the reference's own sums, viscosity.py:212-226) and the oracle.
+# The default route is the direct one; nothing below compares the FFT route with itself.
 @pytest.mark.parametrize("dim,n_dim", [("xyz", 3), ("xz", 2), ("y", 1)])
 def test_helfand_fft_route_against_exact_route(rand_u, dim, n_dim):
     """S1 - 2 S2 cancels; the lags where that costs more than the FP64 bar are re-evaluated exactly (K6), so the FFT
     route meets rtol 1e-10 on every lag of this 700-frame AR(1) trajectory, and row 0 stays exactly 0."""
     u, vel, pos, masses = rand_u
-    exact = VH(u.atoms, dim_type=dim).run()
+    exact = VH(u.atoms, dim_type=dim, fft=False).run()
     fast = VH(u.atoms, dim_type=dim, fft=True).run()
+    assert exact.fft is False and fast.fft is True
+    assert exact._ctx.fft_plan_info()["H"] == 0 and fast._ctx.fft_plan_info()["H"] > 0        # different kernels ran
+    assert fast._ctx.helfand_fft_refined() >= 0                                                # ... and K3 did not take over
     assert fast.results.timeseries[0] == 0.0 and np.all(fast.results.visc_by_particle[0] == 0.0)
     assert_allclose(fast.results.timeseries, exact.results.timeseries, rtol=TOL64)
     assert_allclose(fast.results.visc_by_particle[1:], exact.results.visc_by_particle[1:], rtol=TOL64)
     cols, _ = oracle.parse_dim_type(dim)
-    _, ref_ts = oracle.helfand_msd(_f64(vel)[:, :, cols], _f64(pos)[:, :, cols], masses,
-                                   np.full(len(vel), np.prod(BOX[:3])), 300.0)
-    assert_allclose(fast.results.timeseries, ref_ts, rtol=1e-7)
+    ref_bp, ref_ts = oracle.helfand_msd(_f64(vel)[:, :, cols], _f64(pos)[:, :, cols], masses,
+                                        np.full(len(vel), float(np.prod(np.float32(BOX[:3]).astype(np.float64)))), 300.0)
+    assert_allclose(fast.results.timeseries, ref_ts, rtol=TOL64)
+    assert_allclose(fast.results.visc_by_particle, ref_bp, rtol=TOL64)
+
+
+def test_helfand_default_is_the_direct_route(rand_u):
+    """the O(T log T) route is opt-in; ViscosityHelfand(ag) runs the reference's direct sums (K3)."""
+    u = rand_u[0]
+    h = VH(u.atoms).run()
+    assert h.fft is False and h._ctx.helfand_fft_refined() == 0
+    assert h._ctx.fft_plan_info()["H"] == 0                      # no FFT was planned, let alone launched
 
 
 def test_helfand_fft_route_general_kernel_and_window(rand_u, monkeypatch):
     u, vel, pos, masses = rand_u
-    monkeypatch.setenv("TA_B200_FFT_GENERAL", "1")
-    exact = VH(u.atoms, linear_fit_window=(20, 150)).run(start=3, stop=650, step=2)
+    monkeypatch.setenv("TA_B200_K1_PATH", "general")
+    exact = VH(u.atoms, linear_fit_window=(20, 150), fft=False).run(start=3, stop=650, step=2)
     fast = VH(u.atoms, linear_fit_window=(20, 150), fft=True).run(start=3, stop=650, step=2)
-    assert_allclose(fast.results.timeseries, exact.results.timeseries, rtol=1e-7)
+    assert fast._ctx.fft_plan_info()["radices"][1:] != [16, 16]
+    assert_allclose(fast.results.timeseries, exact.results.timeseries, rtol=TOL64)
     assert_allclose(fast.results.viscosity, exact.results.viscosity, rtol=1e-8)
-    assert_allclose(fast.running_viscosity, exact.running_viscosity, rtol=1e-7)
+    assert_allclose(fast.running_viscosity, exact.running_viscosity, rtol=TOL64)
+
+
+def helfand_fft_threshold(T):
+    """thr of ta_helfand_fft (csrc/ta_b200.cu): a lag is re-evaluated exactly when its un-normalised MSD < thr * sum g^2."""
+    return (100.0 + T / 100.0) * 2.0 ** -53 / 2e-11
 
 
 def _helfand_case(kind, T, N, seed):
-    """Trajectories that stress the S1 - 2 S2 cancellation differently."""
+    """Trajectories that stress the S1 - 2 S2 cancellation differently.  Returns float32 (vel, pos) and masses."""
     rng = np.random.default_rng(seed)
-    if kind == "white":                       # no correlation: MSD ~ 2 var at every lag, only the last lags are delicate
+    masses = np.random.default_rng(1).choice([1.008, 12.011, 15.999], N)
+    thr = helfand_fft_threshold(T)
+    if kind in ("white", "spike1", "spike_all", "masses200"):
+        # no correlation: MSD ~ 2 var at every lag, only the last lags are delicate
         vel = rng.standard_normal((T, N, 3)).astype(np.float32)
         pos = (10.0 * rng.standard_normal((T, N, 3))).astype(np.float32)
+        if kind == "spike1":                  # one huge sample in one particle: its lags > T/2 see none of it
+            vel[T // 2, 0] = 1e4
+        if kind == "spike_all":               # ... in every particle: half of all lags need the exact sum
+            vel[T // 2] = 1e4
+        if kind == "masses200":               # light and heavy particles side by side (1 : 200)
+            masses = np.where(np.arange(N) % 2 == 0, 1.0, 200.0)
     elif kind == "smooth":                    # slowly varying g: MSD << sum g^2 at short lags
         t = np.arange(T)[:, None, None]
         ph = rng.uniform(0, 6.28, (1, N, 3))
@@ -597,26 +582,129 @@ def _helfand_case(kind, T, N, seed):
         vel = np.zeros((T, N, 3), np.float32)
         pos = np.ones((T, N, 3), np.float32)
         vel[:, :3] = rng.standard_normal((T, 3, 3)).astype(np.float32)
-    return vel, pos
+    elif kind in ("offset_above", "offset_below"):
+        # large constant + small noise: MSD[k] / sum g^2 ~ 2 a^2 (T - k) / T, placed a factor 100 above the refinement
+        # threshold (only the last ~1 % of the lags are marked) or a factor 2 below it (every lag is marked)
+        a = np.sqrt((100.0 if kind == "offset_above" else 0.5) * thr / 2.0)
+        vel = (1.0 + a * rng.standard_normal((T, N, 3))).astype(np.float32)
+        pos = np.ones((T, N, 3), np.float32)
+    elif kind == "piecewise":                 # piecewise-constant moments: ten jumps of a tenth of the level
+        level = 1.0 + 0.1 * rng.integers(0, 4, (11, N, 3))
+        vel = np.repeat(level, -(-T // 11), axis=0)[:T].astype(np.float32)
+        pos = np.ones((T, N, 3), np.float32)
+    else:
+        raise ValueError(kind)
+    return vel, pos, masses
 
 
-@pytest.mark.parametrize("kind,T,N", [("white", 3000, 40), ("smooth", 3000, 40), ("walk", 5000, 200), ("ramp", 2000, 3),
-                                      ("frozen", 1600, 12), ("white", 10000, 160), ("smooth", 700, 5)])
-def test_helfand_fft_route_with_exact_refinement_meets_the_fp64_bar(kind, T, N):
+HELFAND_FAMILIES = [("white", 3000, 40, "xyz"), ("smooth", 3000, 40, "xyz"), ("walk", 5000, 200, "xyz"), ("ramp", 2000, 3, "xyz"),
+                    ("frozen", 1600, 12, "xyz"), ("white", 10000, 160, "xyz"), ("smooth", 700, 5, "xyz"),
+                    # adversarial families: spikes, offset + noise either side of the threshold,
+                    # piecewise-constant, one dimension, the longest series K5 holds, masses 1 : 200
+                    ("spike1", 3000, 40, "xyz"), ("spike_all", 3000, 12, "xyz"), ("offset_above", 3000, 24, "xyz"),
+                    ("offset_below", 3000, 24, "xyz"), ("piecewise", 3000, 16, "xyz"), ("white", 4000, 9, "x"),
+                    ("smooth", 5000, 7, "y"), ("white", 28999, 3, "xyz"), ("masses200", 5000, 64, "xyz"),
+                    ("walk", 10000, 24, "xz")]
+
+
+@pytest.mark.parametrize("kind,T,N,dim", HELFAND_FAMILIES)
+def test_helfand_fft_route_with_exact_refinement_meets_the_fp64_bar(kind, T, N, dim):
     """ViscosityHelfand(fft=True): S1 - 2 S2 where it is good to 1e-10, the exact sum (K6) on the lags it marks, the direct
-    kernel when too much is marked -- against the exact route at the FP64 bar (rtol 1e-10), per particle and in the mean."""
-    vel, pos = _helfand_case(kind, T, N, seed=T + N)
-    masses = np.random.default_rng(1).choice([1.008, 12.011, 15.999], N)
+    kernel when too much is marked -- against the DIRECT route (fft=False, K3) on every (lag, particle) and against the
+    oracle on sampled lags, at the FP64 bar (rtol 1e-10); the number of refined lags must be what the criterion predicts."""
+    vel, pos, masses = _helfand_case(kind, T, N, seed=T + N)
     u = make_universe(pos, vel, masses=masses, dimensions=BOX)
-    exact = VH(u.atoms).run()
-    fast = VH(u.atoms, fft=True).run()
+    exact = VH(u.atoms, dim_type=dim, fft=False).run()
+    fast = VH(u.atoms, dim_type=dim, fft=True).run()
+    assert exact.fft is False and fast.fft is True
     refined = fast._ctx.helfand_fft_refined()
     e_bp, f_bp = np.asarray(exact.results.visc_by_particle), np.asarray(fast.results.visc_by_particle)
     assert fast.results.timeseries[0] == 0.0 and np.all(f_bp[0] == 0.0)
     assert_allclose(f_bp, e_bp, rtol=TOL64, atol=0, err_msg=f"{kind}: refined {refined} of {N * T}")
     assert_allclose(fast.results.timeseries, exact.results.timeseries, rtol=TOL64)
-    if kind in ("white", "walk"):
-        assert 0 <= refined < 0.02 * N * T            # the FFT did the work
+    # the oracle on sampled lags, both routes
+    cols, D = oracle.parse_dim_type(dim)
+    lags = sorted({1, 2, 3, 7, T // 10, T // 3, T // 2, T // 2 + 1, (3 * T) // 4, T - 3, T - 2, T - 1})
+    vols = np.full(T, float(np.prod(np.float32(BOX[:3]).astype(np.float64))))
+    ref_bp, _ = oracle.helfand_msd(_f64(vel)[:, :, cols], _f64(pos)[:, :, cols], masses, vols, 300.0, lags=lags)
+    assert_allclose(f_bp[lags], ref_bp[lags], rtol=TOL64, atol=0, err_msg=f"{kind}: FFT route vs oracle")
+    assert_allclose(e_bp[lags], ref_bp[lags], rtol=TOL64, atol=0, err_msg=f"{kind}: direct route vs oracle")
+    # expected number of refined (particle, lag) pairs: un-normalised exact MSD below thr * sum g^2 (K5's criterion),
+    # counted with the threshold 10 % lower / higher to allow for lags that sit on it
+    g = masses[None, :, None] * _f64(vel)[:, :, cols] * _f64(pos)[:, :, cols]
+    tot = (g ** 2).sum(axis=(0, 2))
+    scale = 2 * exact.boltzmann * exact._vol_avg * exact.temp_avg * D
+    msd_un = e_bp[1:] * (T - np.arange(1, T))[:, None] * scale
+    lo = int((msd_un < 0.9 * helfand_fft_threshold(T) * tot[None, :]).sum())
+    hi = int((msd_un < 1.1 * helfand_fft_threshold(T) * tot[None, :]).sum())
+    if lo > 0.02 * N * T:
+        assert refined == -1, f"{kind}: {lo} of {N * T} lags need the exact sum, the direct kernel should have taken over"
+    elif hi <= 0.02 * N * T:
+        assert lo <= refined <= hi, f"{kind}: refined {refined}, criterion predicts {lo}..{hi}"
+    band = {"white": "few", "walk": "few", "masses200": "few", "offset_above": "few", "spike1": "few", "piecewise": "few",
+            "frozen": "few", "spike_all": "all", "offset_below": "all"}.get(kind)
+    if band == "few":
+        assert 0 < refined < 0.02 * N * T, f"{kind}: refined {refined}"            # the FFT did the work
+    if band == "all":
+        assert refined == -1, f"{kind}: refined {refined}"                         # the direct kernel took over
+
+
+def test_helfand_auto_route_falls_back_to_the_direct_sums_beyond_its_length():
+    """fft='auto' on a trajectory longer than the FFT route's finishing kernel holds (T > ~29,000): the direct kernel,
+    and no FFT pass is spent on finding that out."""
+    T, N = 30001, 2
+    vel, pos = random_trajectory(T, N, seed=3, with_positions=True, rho=0.9)
+    u = make_universe(pos, vel, masses=[12.0, 16.0], dimensions=BOX)
+    h = VH(u.atoms, fft="auto")
+    assert h.fft is True
+    h.run()
+    assert h.fft is False
+    assert h._ctx.launch_count() <= 4                 # K0 + K3 + the partial-row sum: no K1
+    lags = [1, 2, 15000, 30000]
+    ref_bp, _ = oracle.helfand_msd(_f64(vel), _f64(pos), np.array([12.0, 16.0]),
+                                   np.full(T, float(np.prod(np.float32(BOX[:3]).astype(np.float64)))), 300.0, lags=lags)
+    assert_allclose(np.asarray(h.results.visc_by_particle)[lags], ref_bp[lags], rtol=TOL64)
+
+
+# ------------------------------------------------------------------ FP32 mode (stated tolerance 1e-5)
+def test_fp32_mode_helfand(rand_u):
+    u, vel, pos, masses = rand_u
+    vols = np.full(700, float(np.prod(np.float32(BOX[:3]).astype(np.float64))))
+    for dim in ("xyz", "y"):
+        cols, _ = oracle.parse_dim_type(dim)
+        ref_bp, ref_ts = oracle.helfand_msd(_f64(vel)[:, :, cols], _f64(pos)[:, :, cols], masses, vols, 300.0)
+        h = VH(u.atoms, dim_type=dim, precision="fp32").run()
+        assert h.results.timeseries[0] == 0.0
+        assert_close_normwise(h.results.timeseries, ref_ts, TOL32, "fp32 Helfand timeseries")
+        assert_close_normwise(h.results.visc_by_particle, ref_bp, TOL32, "fp32 Helfand by particle")
+    with pytest.raises(ValueError, match="fp64"):
+        VH(u.atoms, precision="fp32", fft=True)
+
+
+def test_fp32_mode_at_full_length():
+    """FP32 mode at T = 10,000 (BASELINE configs[3] length), where single-precision accumulation error is largest:
+    FFT route (the three-pass FP32 kernel), windowed route and Helfand against the FP64 oracle at 1e-5 normwise."""
+    T, N = 10000, 12
+    vel, pos = random_trajectory(T, N, seed=77, with_positions=True, rho=0.9)
+    masses = np.random.default_rng(5).choice([1.008, 12.011, 15.999], N)
+    u = make_universe(pos, vel, masses=masses, dimensions=BOX)
+    ref_bp, ref_ts = oracle.vacf_fft(_f64(vel))
+    for fft in (True, False):
+        v = VACF(u.atoms, fft=fft, precision="fp32").run()
+        if fft:
+            assert v._ctx.fft_plan_info()["radices"] == [20, 16, 16]
+        # FFT route: the float rounding floor of the un-normalised correlation is divided by the number of origins, so
+        # the stated 1e-5 covers the lags with at least 8 origins and the last 8 are within 1e-4 (DESIGN.md "FP32 mode")
+        cut = -8 if fft else None
+        assert_close_normwise(v.results.timeseries[:cut], ref_ts[:cut], TOL32, f"fp32 fft={fft} timeseries")
+        assert_close_normwise(v.results.vacf_by_particle[:cut], ref_bp[:cut], TOL32, f"fp32 fft={fft} by particle")
+        assert_close_normwise(v.results.vacf_by_particle, ref_bp, 1e-4, f"fp32 fft={fft} by particle, last lags")
+    lags = [1, 2, 100, 2500, 5000, 7500, 9990, 9999]
+    vols = np.full(T, float(np.prod(np.float32(BOX[:3]).astype(np.float64))))
+    ref_h, _ = oracle.helfand_msd(_f64(vel), _f64(pos), masses, vols, 300.0, lags=lags)
+    h = VH(u.atoms, precision="fp32").run()
+    hb = np.asarray(h.results.visc_by_particle)
+    assert_close_normwise(hb[lags], ref_h[lags], TOL32, "fp32 Helfand by particle")
 
 
 # ------------------------------------------------------------------ series longer than shared memory (direct routes)

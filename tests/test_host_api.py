@@ -145,12 +145,14 @@ def test_helfand_fft_route_needs_fp64(u):
 
 
 def test_helfand_route_argument(u):
-    """fft='auto' (default): the FFT route with exact refinement in FP64, the direct lag sums in the FP32 mode;
-    True / False force a route; anything else is refused."""
-    assert VH(u.atoms).fft is True and VH(u.atoms)._fft_auto
+    """fft=False (default): the reference's direct lag sums.  True: the O(T log T) route with exact
+    refinement (FP64 only).  'auto': that route where it applies, the direct sums in the FP32 mode.  Anything else is
+    refused."""
+    assert VH(u.atoms).fft is False and not VH(u.atoms)._fft_auto
     assert VH(u.atoms, precision="fp32").fft is False
-    assert VH(u.atoms, fft=False).fft is False and not VH(u.atoms, fft=False)._fft_auto
-    assert VH(u.atoms, fft=True).fft is True
+    assert VH(u.atoms, fft="auto").fft is True and VH(u.atoms, fft="auto")._fft_auto
+    assert VH(u.atoms, fft="auto", precision="fp32").fft is False
+    assert VH(u.atoms, fft=True).fft is True and not VH(u.atoms, fft=True)._fft_auto
     for bad in ("yes", 2, None):
         with pytest.raises(ValueError, match="fft must be"):
             VH(u.atoms, fft=bad)

@@ -140,7 +140,7 @@ def test_helfand_asks_for_both_fields_masses_and_volumes(fake):
     assert bulk[1] == [(7, 4, 3), (7, 4, 3)]                                        # velocities, then positions
     call = [c for c in fake.calls if c[0] == "helfand"][0]
     np.testing.assert_allclose(call[1], np.full(7, 24.0))
-    assert call[3] == 250.0 and call[4] is True                                     # default route: FFT + exact refinement
+    assert call[3] == 250.0 and call[4] is False                                    # default route: the direct lag sums
     # the linear fit of the reference (viscosity.py:235-245): x starts at lag 1, y at lag 0 -> slope of y = 2 k is 2
     assert h.results.viscosity == pytest.approx(2.0)
 

@@ -89,48 +89,57 @@ TA_HD void static_for(F&& f) {
 }
 
 using cd = cplx<double>;
+using cf = cplx<float>;
+
+// real type of a complex value type
+template <class C> struct real_of;
+template <class R> struct real_of<cplx<R>> { using type = R; };
+template <class C> using real_t = typename real_of<C>::type;
 
 // a * exp(DIR * 2 pi i K / N), constant folded; axis and diagonal cases are cheaper
-template <int K, int N, int DIR>
-TA_HD cd mul_tw(cd a) {
+template <int K, int N, int DIR, class C>
+TA_HD C mul_tw(C a) {
+    using R = real_t<C>;
     constexpr long long k = ct::pmod(K, N);
     if constexpr (k == 0) {
         return a;
     } else if constexpr (2 * k == N) {
-        return cmake<double>(-a.x, -a.y);
+        return cmake<R>(-a.x, -a.y);
     } else if constexpr (4 * k == N) {               // exp(DIR i pi/2) = DIR i
         return DIR < 0 ? cmul_mi(a) : cmul_pi(a);
     } else if constexpr (4 * k == 3 * N) {           // exp(DIR i 3pi/2) = -DIR i
         return DIR < 0 ? cmul_pi(a) : cmul_mi(a);
     } else {
-        constexpr double c = ct::cos2pi(k, N);
-        constexpr double s = (DIR < 0 ? -1.0 : 1.0) * ct::sin2pi(k, N);
-        return cmake<double>(a.x * c - a.y * s, a.x * s + a.y * c);
+        constexpr R c = (R)ct::cos2pi(k, N);
+        constexpr R s = (R)((DIR < 0 ? -1.0 : 1.0) * ct::sin2pi(k, N));
+        return cmake<R>(a.x * c - a.y * s, a.x * s + a.y * c);
     }
 }
 
 template <int N, int DIR> struct Dft;
 
 template <int DIR> struct Dft<1, DIR> {
-    static TA_HD void run(cd*) {}
+    template <class C> static TA_HD void run(C*) {}
 };
 
 template <int DIR> struct Dft<2, DIR> {
-    static TA_HD void run(cd* v) {
-        cd t = csub(v[0], v[1]);
+    template <class C> static TA_HD void run(C* v) {
+        C t = csub(v[0], v[1]);
         v[0] = cadd(v[0], v[1]);
         v[1] = t;
     }
 };
 
 template <int DIR> struct Dft<3, DIR> {
-    static TA_HD void run(cd* v) {
-        constexpr double hs3 = 0.86602540378443864676372317075294;   // sin(pi/3)
-        cd t = cadd(v[1], v[2]);
-        cd u = csub(v[1], v[2]);
-        cd m = cmake<double>(v[0].x - 0.5 * t.x, v[0].y - 0.5 * t.y);
-        cd su = cmake<double>(hs3 * u.x, hs3 * u.y);
-        cd ru = DIR < 0 ? cmul_mi(su) : cmul_pi(su);
+    template <class C> static TA_HD void run(C* v) {
+        using R = real_t<C>;
+        constexpr R hs3 = (R)0.86602540378443864676372317075294;   // sin(pi/3)
+        constexpr R half = (R)0.5;
+        C t = cadd(v[1], v[2]);
+        C u = csub(v[1], v[2]);
+        C m = cmake<R>(v[0].x - half * t.x, v[0].y - half * t.y);
+        C su = cmake<R>(hs3 * u.x, hs3 * u.y);
+        C ru = DIR < 0 ? cmul_mi(su) : cmul_pi(su);
         v[0] = cadd(v[0], t);
         v[1] = cadd(m, ru);
         v[2] = csub(m, ru);
@@ -138,10 +147,10 @@ template <int DIR> struct Dft<3, DIR> {
 };
 
 template <int DIR> struct Dft<4, DIR> {
-    static TA_HD void run(cd* v) {
-        cd t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
-        cd t2 = cadd(v[1], v[3]), d = csub(v[1], v[3]);
-        cd t3 = DIR < 0 ? cmul_mi(d) : cmul_pi(d);
+    template <class C> static TA_HD void run(C* v) {
+        C t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
+        C t2 = cadd(v[1], v[3]), d = csub(v[1], v[3]);
+        C t3 = DIR < 0 ? cmul_mi(d) : cmul_pi(d);
         v[0] = cadd(t0, t2);
         v[1] = cadd(t1, t3);
         v[2] = csub(t0, t2);
@@ -150,20 +159,21 @@ template <int DIR> struct Dft<4, DIR> {
 };
 
 template <int DIR> struct Dft<5, DIR> {
-    static TA_HD void run(cd* v) {
-        constexpr double c1 = 0.30901699437494742410229341718282;    // cos(2pi/5)
-        constexpr double c2 = -0.80901699437494742410229341718282;   // cos(4pi/5)
-        constexpr double s1 = 0.95105651629515357211643933337938;    // sin(2pi/5)
-        constexpr double s2 = 0.58778525229247312916870595463907;    // sin(4pi/5)
-        cd t1 = cadd(v[1], v[4]), t2 = cadd(v[2], v[3]);
-        cd t3 = csub(v[1], v[4]), t4 = csub(v[2], v[3]);
-        cd a1 = cmake<double>(v[0].x + c1 * t1.x + c2 * t2.x, v[0].y + c1 * t1.y + c2 * t2.y);
-        cd a2 = cmake<double>(v[0].x + c2 * t1.x + c1 * t2.x, v[0].y + c2 * t1.y + c1 * t2.y);
-        cd q1 = cmake<double>(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
-        cd q2 = cmake<double>(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
-        cd b1 = DIR < 0 ? cmul_mi(q1) : cmul_pi(q1);
-        cd b2 = DIR < 0 ? cmul_mi(q2) : cmul_pi(q2);
-        v[0] = cmake<double>(v[0].x + t1.x + t2.x, v[0].y + t1.y + t2.y);
+    template <class C> static TA_HD void run(C* v) {
+        using R = real_t<C>;
+        constexpr R c1 = (R)0.30901699437494742410229341718282;    // cos(2pi/5)
+        constexpr R c2 = (R)-0.80901699437494742410229341718282;   // cos(4pi/5)
+        constexpr R s1 = (R)0.95105651629515357211643933337938;    // sin(2pi/5)
+        constexpr R s2 = (R)0.58778525229247312916870595463907;    // sin(4pi/5)
+        C t1 = cadd(v[1], v[4]), t2 = cadd(v[2], v[3]);
+        C t3 = csub(v[1], v[4]), t4 = csub(v[2], v[3]);
+        C a1 = cmake<R>(v[0].x + c1 * t1.x + c2 * t2.x, v[0].y + c1 * t1.y + c2 * t2.y);
+        C a2 = cmake<R>(v[0].x + c2 * t1.x + c1 * t2.x, v[0].y + c2 * t1.y + c1 * t2.y);
+        C q1 = cmake<R>(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
+        C q2 = cmake<R>(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
+        C b1 = DIR < 0 ? cmul_mi(q1) : cmul_pi(q1);
+        C b2 = DIR < 0 ? cmul_mi(q2) : cmul_pi(q2);
+        v[0] = cmake<R>(v[0].x + t1.x + t2.x, v[0].y + t1.y + t2.y);
         v[1] = cadd(a1, b1);
         v[4] = csub(a1, b1);
         v[2] = cadd(a2, b2);
@@ -176,12 +186,12 @@ template <int DIR> struct Dft<5, DIR> {
 //   y[k1 + B k2] = sum_a w_A^{a k2} ( w_N^{a k1} sum_m x[A m + a] w_B^{m k1} )
 template <int A, int B, int DIR>
 struct DftComposite {
-    static TA_HD void run(cd* v) {
+    template <class C> static TA_HD void run(C* v) {
         constexpr int N = A * B;
-        cd u[N];   // u[a * B + k1]
+        C u[N];   // u[a * B + k1]
         static_for<0, A>([&](auto ia) {
             constexpr int a = decltype(ia)::value;
-            cd t[B];
+            C t[B];
             static_for<0, B>([&](auto im) {
                 constexpr int m = decltype(im)::value;
                 t[m] = v[A * m + a];
@@ -194,7 +204,7 @@ struct DftComposite {
         });
         static_for<0, B>([&](auto ik) {
             constexpr int k1 = decltype(ik)::value;
-            cd s[A];
+            C s[A];
             static_for<0, A>([&](auto ia) {
                 constexpr int a = decltype(ia)::value;
                 s[a] = u[a * B + k1];
@@ -204,58 +214,6 @@ struct DftComposite {
                 constexpr int k2 = decltype(ik2)::value;
                 v[k1 + B * k2] = s[k2];
             });
-        });
-    }
-};
-
-// ---------------------------------------------------------------------------
-// Radix-16 butterfly with a power sequence of one run-time twiddle on its inputs,
-//   y[k] = sum_q u[q] om^q exp(DIR 2 pi i q k / 16),
-// as four layers of radix-2 steps a +- t b in which the twiddle rides on the multiply of a fused multiply-add
-// (6 FMAs per step: p = a + t b, m = 2 a - p; 192 instructions instead of 60 for the multiplications by om^q plus 160
-// for the plain DFT).  Splitting the INPUT index by its top bit, q = q' + (M/2) b,
-//   y[2k']   = sum_q' (u[q'] + beta^(M/2) u[q'+M/2]) beta^q' w_(M/2)^(q'k')
-//   y[2k'+1] = sum_q' (u[q'] - beta^(M/2) u[q'+M/2]) (beta w_M)^q' w_(M/2)^(q'k')
-// every step of a layer uses beta^(M/2) = om^(M/2) w_16^(E M/2) with beta = om w_16^E, so the 32 steps draw on only eight
-// values: T = { om^8, om^4, om^2, om^2 w_8, om, om w_16, om w_16^2, om w_16^3 } (forward w = exp(-2 pi i / .)), each possibly
-// turned by a power of i, which costs nothing.  CONJ uses conj(T): the table of the inverse transform (DIR = +1).
-// T is read with stride TS at the point of use, so that no more than one or two twiddles are live at a time.
-// ---------------------------------------------------------------------------
-template <int ROT, bool CONJ, int DIR>
-TA_HD void bfly_tw(cd& a, cd& b, const cd tw) {
-    const double tx = tw.x, ty = CONJ ? -tw.y : tw.y;
-    constexpr int rr = ((ROT % 4) + 4) % 4;          // t = (tx + i ty) (DIR i)^rr
-    const double ux = rr == 0 ? tx : rr == 2 ? -tx : ((rr == 1) == (DIR > 0) ? -ty : ty);
-    const double uy = rr == 0 ? ty : rr == 2 ? -ty : ((rr == 1) == (DIR > 0) ? tx : -tx);
-    double px = fma(ux, b.x, a.x), py = fma(ux, b.y, a.y);
-    px = fma(-uy, b.y, px);
-    py = fma(uy, b.x, py);
-    b = cmake<double>(fma(2.0, a.x, -px), fma(2.0, a.y, -py));
-    a = cmake<double>(px, py);
-}
-
-template <int M, int E, int DIR, bool CONJ, int TS>
-struct TwDit {
-    static TA_HD void run(cd* u, const cd* T) {
-        constexpr int h = M / 2;
-        constexpr int ti = M == 16 ? 0 : M == 8 ? 1 : M == 4 ? (2 + (E & 1)) : (4 + (E & 3));
-        constexpr int rot = M == 16 ? 0 : M == 8 ? E : M == 4 ? (E >> 1) : (E >> 2);
-        cd a[h], b[h];
-        const cd t = T[ti * TS];
-        static_for<0, h>([&](auto iq) {
-            constexpr int q = decltype(iq)::value;
-            a[q] = u[q];
-            b[q] = u[q + h];
-            bfly_tw<rot, CONJ, DIR>(a[q], b[q], t);
-        });
-        if constexpr (h > 1) {
-            TwDit<h, E, DIR, CONJ, TS>::run(a, T);
-            TwDit<h, E + 16 / M, DIR, CONJ, TS>::run(b, T);
-        }
-        static_for<0, h>([&](auto ik) {
-            constexpr int k = decltype(ik)::value;
-            u[2 * k] = a[k];
-            u[2 * k + 1] = b[k];
         });
     }
 };

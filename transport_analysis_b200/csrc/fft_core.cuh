@@ -195,19 +195,18 @@ TA_HD void dit_pass_any(int radix, int tid, int nthr, cplx<R>* buf, const FftTab
 }
 
 // ---------------------------------------------------------------------------
-// Phase: load one real series (length T, stored as doubles, zero beyond T up to
+// Phase: load one real series (length T, stored in the arithmetic type R, zero beyond T up to
 // the next even index) as z[n] = x[2n] + i x[2n+1], n < H, twisted by
 // w_{2H}^{n} = w_L^{2n} for the odd residue.
 // ---------------------------------------------------------------------------
 template <typename R>
-TA_HD void fft_load(int tid, int nthr, cplx<R>* buf, const double* series, const FftTables<R>& t, int r) {
+TA_HD void fft_load(int tid, int nthr, cplx<R>* buf, const R* series, const FftTables<R>& t, int r) {
     const int nh = (t.T + 1) / 2;
-    const cplx<double>* src = reinterpret_cast<const cplx<double>*>(series);
+    const cplx<R>* src = reinterpret_cast<const cplx<R>*>(series);
     for (int n = tid; n < t.H; n += nthr) {
         cplx<R> z = cmake<R>((R)0, (R)0);
         if (n < nh) {
-            cplx<double> v = src[n];
-            z = cmake<R>((R)v.x, (R)v.y);
+            z = src[n];
             if (r) z = cmul(z, tw_get(t, 2 * n));
         }
         buf[n] = z;

@@ -9,7 +9,6 @@
 #include "fft_core.cuh"
 #include "windowed_core.cuh"
 #include "k1_fast.cuh"
-#include "k1_r8.cuh"
 
 namespace ta {
 
@@ -25,36 +24,39 @@ namespace ta {
 constexpr int K0_FR = 32;   // frames per tile
 constexpr int K0_AT = 32;   // atoms per tile
 
-template <typename SRC, bool HELFAND>
+template <typename SRC, bool HELFAND, typename OUT>
 __global__ void __launch_bounds__(256)
 k0_stage(const SRC* __restrict__ v, const SRC* __restrict__ x, const double* __restrict__ masses,
-         double* __restrict__ series, int natoms, int nframes, long long frame0, long long Tld,
+         OUT* __restrict__ series, int natoms, int nframes, long long frame0, long long Tld,
          int D, int d0, int d1, int d2) {
-    __shared__ double tile[K0_FR][K0_AT * 3 + 1];
-    const int a0 = blockIdx.x * K0_AT;
-    const int f0 = blockIdx.y * K0_FR;
-    const int na = min(K0_AT, natoms - a0);
+    // frames on grid.x (2^31 - 1 tiles: any T the library accepts), particles on grid.y, tiled further by the loop below
+    __shared__ OUT tile[K0_FR][K0_AT * 3 + 1];
+    const int f0 = blockIdx.x * K0_FR;
     const int nf = min(K0_FR, nframes - f0);
-    const int ncol = na * 3;
-    for (int f = threadIdx.y; f < nf; f += blockDim.y) {
-        const size_t rowoff = ((size_t)(f0 + f) * natoms + a0) * 3;
-        for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
-            double val = (double)v[rowoff + c];
-            if (HELFAND) {
-                double m = masses[a0 + c / 3];
-                val = (m * val) * (double)x[rowoff + c];
-            }
-            tile[f][c] = val;
-        }
-    }
-    __syncthreads();
     const int dims[3] = {d0, d1, d2};
-    const int nrows = na * D;
-    for (int r = threadIdx.y; r < nrows; r += blockDim.y) {
-        const int a = r / D, d = r - a * D;
-        double* dst = series + ((size_t)(a0 + a) * D + d) * Tld + frame0 + f0;
-        const int col = a * 3 + dims[d];
-        for (int f = threadIdx.x; f < nf; f += blockDim.x) dst[f] = tile[f][col];
+    for (int a0 = blockIdx.y * K0_AT; a0 < natoms; a0 += gridDim.y * K0_AT) {
+        const int na = min(K0_AT, natoms - a0);
+        const int ncol = na * 3;
+        for (int f = threadIdx.y; f < nf; f += blockDim.y) {
+            const size_t rowoff = ((size_t)(f0 + f) * natoms + a0) * 3;
+            for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
+                double val = (double)v[rowoff + c];
+                if (HELFAND) {
+                    double m = masses[a0 + c / 3];
+                    val = (m * val) * (double)x[rowoff + c];
+                }
+                tile[f][c] = (OUT)val;
+            }
+        }
+        __syncthreads();
+        const int nrows = na * D;
+        for (int r = threadIdx.y; r < nrows; r += blockDim.y) {
+            const int a = r / D, d = r - a * D;
+            OUT* dst = series + ((size_t)(a0 + a) * D + d) * Tld + frame0 + f0;
+            const int col = a * 3 + dims[d];
+            for (int f = threadIdx.x; f < nf; f += blockDim.x) dst[f] = tile[f][col];
+        }
+        __syncthreads();
     }
 }
 
@@ -65,7 +67,7 @@ template <typename R>
 struct K1Args {
     FftTables<R> t;              // tw_lo / tw_hi point to GLOBAL copies here
     int nlo, nhi;
-    const double* series;        // [natoms][D][Tld]
+    const R* series;             // [natoms][D][Tld]  (stored in the arithmetic type)
     double* by_particle;         // [natoms][Tld]
     double* partial;             // [gridDim.x][Tld]
     int natoms, D;
@@ -100,7 +102,7 @@ k1_fft_acf(const K1Args<R> args) {
 
     double* partial = args.partial + (size_t)blockIdx.x * args.Tld;
     for (int a = blockIdx.x; a < args.natoms; a += gridDim.x) {
-        const double* ser = args.series + (size_t)a * args.D * args.Tld;
+        const R* ser = args.series + (size_t)a * args.D * args.Tld;
         double* row = args.by_particle + (size_t)a * args.Tld;
         for (int r = 0; r < 2; ++r) {
             fft_zero_acc<R>(tid, nthr, sd, t);
@@ -133,6 +135,7 @@ k1_fft_acf(const K1Args<R> args) {
 
 // ---------------------------------------------------------------------------
 // K1 fast path (k1_fast.cuh): H = 256 R1 in three register-DFT passes.
+// DevCtx: the device side of the `Ctx` policy the kernel bodies are written against (tests/emu has the CPU side).
 // ---------------------------------------------------------------------------
 struct DevCtx {
     static TA_HD void sync() {
@@ -145,14 +148,14 @@ struct DevCtx {
         __syncwarp();
 #endif
     }
-    static TA_HD double shfl_xor(double v, int mask) {
+    template <class V> static TA_HD V shfl_xor(V v, int mask) {
 #if defined(__CUDA_ARCH__)
         return __shfl_xor_sync(0xffffffffu, v, mask);
 #else
         return v;
 #endif
     }
-    static TA_HD double shfl_xor16(double v) {
+    template <class V> static TA_HD V shfl_xor16(V v) {
 #if defined(__CUDA_ARCH__)
         return __shfl_xor_sync(0xffffffffu, v, 16);
 #else
@@ -168,48 +171,17 @@ struct DevCtx {
         return *p;
 #endif
     }
+    static TA_HD cf ld_stream(const cf* p) {
+#if defined(__CUDA_ARCH__)
+        const float2 v = __ldcg(reinterpret_cast<const float2*>(p));
+        return cmake<float>(v.x, v.y);
+#else
+        return *p;
+#endif
+    }
     static TA_HD void compiler_fence() {
 #if defined(__CUDA_ARCH__)
         asm volatile("" ::: "memory");
-#endif
-    }
-    // named barriers (ids 1..15; id 0 is __syncthreads): wait for / signal `count` threads
-    static TA_HD void bar_sync(int id, int count) {
-#if defined(__CUDA_ARCH__)
-        asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-#endif
-    }
-    static TA_HD void bar_arrive(int id, int count) {
-#if defined(__CUDA_ARCH__)
-        asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
-#endif
-    }
-    // 1 / a for a > 0: hardware seed + two Newton steps (within 1 ulp; no table, no division sequence)
-    static TA_HD double rcp(double a) {
-#if defined(__CUDA_ARCH__)
-        double y;
-        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-        double e = fma(-a, y, 1.0);
-        y = fma(y, e, y);
-        e = fma(-a, y, 1.0);
-        return fma(y, e, y);
-#else
-        return 1.0 / a;
-#endif
-    }
-    // shared-memory writes of this thread become visible to the bulk-copy (async) proxy
-    static TA_HD void fence_async_smem() {
-#if defined(__CUDA_ARCH__)
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#endif
-    }
-    // one bulk group: row[0..bytes) = src, part[0..bytes) += src (f64 reduce-add at L2); src is shared memory
-    static TA_HD void bulk_store_and_add(cd* row, cd* part, const cd* src, unsigned bytes) {
-#if defined(__CUDA_ARCH__)
-        const unsigned s = (unsigned)__cvta_generic_to_shared(src);
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(row), "r"(s), "r"(bytes) : "memory");
-        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(part), "r"(s), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 #endif
     }
     // mbarrier with one arrival per phase (the thread that issues the bulk load)
@@ -220,8 +192,8 @@ struct DevCtx {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #endif
     }
-    // dst[0..bytes) (shared) <- src (global) by the bulk-copy engine; completion flips the phase of `bar`
-    static TA_HD void bulk_load(cd* dst, const double* src, unsigned bytes, unsigned long long* bar) {
+    // dst[0..bytes) (shared) <- src (global) by the bulk-copy engine (TMA); completion flips the phase of `bar`
+    static TA_HD void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
 #if defined(__CUDA_ARCH__)
         const unsigned a = (unsigned)__cvta_generic_to_shared(bar), d = (unsigned)__cvta_generic_to_shared(dst);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
@@ -239,93 +211,29 @@ struct DevCtx {
         }
 #endif
     }
-    // all bulk groups of this thread have completed (source read and destination written)
-    static TA_HD void bulk_wait_all() {
-#if defined(__CUDA_ARCH__)
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-#endif
-    }
-    static TA_HD long long clock_after(double dep) {
-#if defined(__CUDA_ARCH__)
-        long long t;
-        asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "d"(dep) : "memory");
-        return t;
-#else
-        return 0;
-#endif
-    }
-    static TA_HD void spin(int clocks) {
-#if defined(__CUDA_ARCH__)
-        const long long t0 = clock64();
-        while (clock64() - t0 < clocks) {}
-        __syncthreads();
-#endif
-    }
-    // the CTA that arrives second (fourth, ...) on its SM idles for `clocks` before it starts
-    static TA_HD void stagger_second_cta(unsigned* sm_slots, int clocks, int tid) {
-#if defined(__CUDA_ARCH__)
-        __shared__ unsigned s_slot;
-        if (tid == 0) {
-            unsigned smid;
-            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            s_slot = atomicAdd(sm_slots + smid, 1u);
-        }
-        __syncthreads();
-        if (s_slot & 1u) {
-            const long long t0 = clock64();
-            while (clock64() - t0 < clocks) {}
-        }
-        __syncthreads();
-#endif
-    }
-    static TA_HD long long clock() {
-#if defined(__CUDA_ARCH__)
-        return clock64();
-#else
-        return 0;
-#endif
-    }
-    // ask L2 for `bytes` at p (the next particle's series); 4 KB per participating thread
-    static TA_HD void prefetch_l2(const void* p, size_t bytes, int tid, int nthr) {
-#if defined(__CUDA_ARCH__)
-        const char* c = static_cast<const char*>(p);
-        for (size_t off = (size_t)tid * 4096; off < bytes; off += (size_t)nthr * 4096) {
-            const unsigned n = (unsigned)((bytes - off) < 4096 ? (bytes - off) & ~(size_t)15 : 4096);
-            if (n) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(c + off), "r"(n) : "memory");
-        }
-#endif
-    }
 };
 
-template <int R1, int NT, bool PROF = false, int VAR = 0>
-__global__ void __launch_bounds__(NT, k1f_min_blocks(NT))
-k1f_fft_acf(const K1FArgs args) {
+// One kernel per (R1, arithmetic type).  NT = 16 R1 threads; the bulk series prefetch where k1f_prefetch says so.
+template <int R1, typename RT>
+__global__ void __launch_bounds__(k1f_threads(R1), k1f_min_blocks(k1f_threads(R1), (int)sizeof(RT)))
+k1f_fft_acf(const K1FArgs<RT> args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    k1f_body<R1, NT, DevCtx, PROF, VAR>(args, smem_raw, (int)threadIdx.x, (int)blockIdx.x, (int)gridDim.x);
+    k1f_body<R1, k1f_threads(R1), DevCtx, RT, k1f_prefetch(R1, (int)sizeof(RT))>(args, smem_raw, (int)threadIdx.x, (int)blockIdx.x,
+                                                                                 (int)gridDim.x);
 }
 
-// The same kernel with the register cap stated outright instead of derived from launch bounds.  With ten warps per SM
-// (three on two of the sub-partitions, 16,384 registers each) 170 registers per thread is the ceiling either way, but ptxas
-// schedules differently under the two attributes: __launch_bounds__(320, 1) gives 168 registers and 16-32 B of spills,
-// __maxnreg__(184) 166 registers and none -- 24.2 -> 23.5 ms at 100k x 10k (caps 152 / 160 / 168 / 176 / 184: 24.21 / 24.08 /
-// 23.66 / 23.52 / 23.46 ms; 200 does not fit).  Used for NT = 320 (R1 = 20) only: at NT = 160 the same cap yields 174
-// registers, which would leave one CTA per SM instead of two.
+// The FP64 kernel of ten warps (R1 = 20) with the register cap stated outright instead of derived from launch bounds.
+// With three warps on two of the sub-partitions (16,384 registers each) 170 registers per thread is the ceiling either
+// way, but ptxas schedules differently under the two attributes: __launch_bounds__(320, 1) gives 168 registers and
+// 16-32 B of spills, __maxnreg__(184) 166 registers and none -- 24.2 -> 23.5 ms at 100k x 10k (caps 152 / 160 / 168 /
+// 176 / 184: 24.21 / 24.08 / 23.66 / 23.52 / 23.46 ms; 200 does not fit).
 constexpr int K1F_MAXREG = 184;
-template <int R1, int NT, int VAR, int MAXREG>
-__global__ void __maxnreg__(MAXREG)
-k1f_fft_acf_mr(const K1FArgs args) {
+template <int R1, typename RT>
+__global__ void __maxnreg__(K1F_MAXREG)
+k1f_fft_acf_mr(const K1FArgs<RT> args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    k1f_body<R1, NT, DevCtx, false, VAR>(args, smem_raw, (int)threadIdx.x, (int)blockIdx.x, (int)gridDim.x);
-}
-
-// ---------------------------------------------------------------------------
-// K1 radix-8 path (k1_r8.cuh): H = 512 R in four passes, 64 R threads, one CTA per SM.
-// ---------------------------------------------------------------------------
-template <int R>
-__global__ void __launch_bounds__(64 * R, R <= 5 ? 2 : 1)
-k1e_fft_acf(const K1EArgs args) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    k1e_body<R, DevCtx>(args, smem_raw, (int)threadIdx.x, (int)blockIdx.x, (int)gridDim.x);
+    k1f_body<R1, k1f_threads(R1), DevCtx, RT, k1f_prefetch(R1, (int)sizeof(RT))>(args, smem_raw, (int)threadIdx.x, (int)blockIdx.x,
+                                                                                 (int)gridDim.x);
 }
 
 // ---------------------------------------------------------------------------

@@ -89,7 +89,7 @@ struct Shard {
     // problem-sized state
     int64_t atom0 = 0, natoms = 0;
     double natoms_d = 0.0;
-    double* series = nullptr;
+    void* series = nullptr;             // [natoms][D][Tld] of double (FP64) or float (FP32 mode)
     double* by_particle = nullptr;
     double* masses = nullptr;
     double* ts_sum = nullptr;
@@ -115,20 +115,12 @@ struct Shard {
     uint32_t* ftab = nullptr;
     uint32_t* pair0 = nullptr;
     uint32_t* own0 = nullptr;
-    // fast-path FFT tables (k1_fast.cuh)
+    // fast-path FFT tables (k1_fast.cuh), in the arithmetic type of the plan
     void* f_omega = nullptr;
     void* f_tw2 = nullptr;
-    void* f_tw8 = nullptr;
     uint32_t* f_map = nullptr;
     void* f_wbase = nullptr;
-    double* f_inv = nullptr;
-    // radix-8 path FFT tables (k1_r8.cuh)
-    void* e_omega = nullptr;
-    void* e_tw2 = nullptr;
-    void* e_tw3 = nullptr;
-    uint32_t* e_map = nullptr;
-    void* e_wbase = nullptr;
-    unsigned* e_slots = nullptr;        // [1024] per-SM CTA arrival counters (stagger of co-resident CTAs)
+    void* f_inv = nullptr;
     // FFT route of the Helfand MSD: per-particle bitmaps of the lags that need the exact evaluation (+ a counter)
     uint32_t* hflags = nullptr;
     size_t hflags_bytes = 0;
@@ -160,7 +152,14 @@ struct ta_ctx {
     int plan_prec = -1;
     int npairs0 = 0;
     int fast_r1 = 0;         // > 0: the plan is for the three-pass path (k1_fast.cuh) with this R1
-    int fast_r8 = 0;         // > 0: the plan is for the radix-8 path (k1_r8.cuh) with this R
+    // debugging knobs, read from the environment ONCE when the context is created (never on a launch path):
+    //   TA_B200_K1_PATH = general        the general mixed-radix FFT kernel even where the three-pass kernel applies
+    //                                    (the tests compare the two kernels with each other)
+    //   TA_B200_BULK_CHUNK = n           particles per staging chunk of ta_stage_bulk (tests: any chunking, same bits)
+    //   TA_B200_HELFAND_FFT_THR = x      refinement threshold of ta_helfand_fft (scripts/helfand_fft_error_constant.py)
+    bool opt_general_fft = false;
+    int64_t opt_bulk_chunk = 0;
+    double opt_helfand_thr = -2.0;       // < -1.5: the built-in rule
     int k1_threads = 0, k1_smem = 0, k1_grid = 0;
     std::vector<double> host_ts;
     int64_t launches = 0;
@@ -217,16 +216,9 @@ void free_problem(ta_ctx* c) {
         cudaFree(s.own0); s.own0 = nullptr;
         cudaFree(s.f_omega); s.f_omega = nullptr;
         cudaFree(s.f_tw2); s.f_tw2 = nullptr;
-        cudaFree(s.f_tw8); s.f_tw8 = nullptr;
         cudaFree(s.f_map); s.f_map = nullptr;
         cudaFree(s.f_wbase); s.f_wbase = nullptr;
         cudaFree(s.f_inv); s.f_inv = nullptr;
-        cudaFree(s.e_omega); s.e_omega = nullptr;
-        cudaFree(s.e_tw2); s.e_tw2 = nullptr;
-        cudaFree(s.e_tw3); s.e_tw3 = nullptr;
-        cudaFree(s.e_map); s.e_map = nullptr;
-        cudaFree(s.e_wbase); s.e_wbase = nullptr;
-        cudaFree(s.e_slots); s.e_slots = nullptr;
         cudaFree(s.hflags); s.hflags = nullptr; s.hflags_bytes = 0;
     }
     for (int i = 0; i < kNumSlabs; ++i) {
@@ -279,28 +271,31 @@ int sync_all(ta_ctx* ctx) {
 }
 
 // K0 on `stream`: staged slab [nframes][n][3] (particles a0 .. a0+n-1 of the shard) -> series.
-int launch_k0(ta_ctx* ctx, Shard& s, const void* vsrc, const void* xsrc, int64_t a0, int64_t n, int64_t nframes,
-              int64_t frame0, cudaStream_t stream) {
+template <typename SRC, typename OUT>
+int launch_k0_t(ta_ctx* ctx, Shard& s, const void* vsrc, const void* xsrc, int64_t a0, int64_t n, int64_t nframes,
+                int64_t frame0, cudaStream_t stream) {
     dim3 block(32, 8);
-    dim3 grid((unsigned)((n + K0_AT - 1) / K0_AT), (unsigned)((nframes + K0_FR - 1) / K0_FR));
+    // frames on grid.x (up to 2^31 - 1 tiles), particle tiles on grid.y (the kernel loops when there are more than 65,535)
+    dim3 grid((unsigned)((nframes + K0_FR - 1) / K0_FR), (unsigned)std::min<int64_t>((n + K0_AT - 1) / K0_AT, 65535));
     const int d0 = ctx->dims[0], d1 = ctx->dims[1], d2 = ctx->dims[2];
-    const bool hel = ctx->n_fields == 2;
-    double* series = s.series + (size_t)a0 * ctx->D * ctx->Tld;
+    OUT* series = (OUT*)s.series + (size_t)a0 * ctx->D * ctx->Tld;
     const double* masses = s.masses ? s.masses + a0 : nullptr;
-    if (ctx->src_dtype == TA_DTYPE_F32) {
-        const float* v = (const float*)vsrc;
-        const float* x = (const float*)xsrc;
-        if (hel) k0_stage<float, true><<<grid, block, 0, stream>>>(v, x, masses, series, (int)n, (int)nframes, frame0, ctx->Tld, ctx->D, d0, d1, d2);
-        else k0_stage<float, false><<<grid, block, 0, stream>>>(v, x, masses, series, (int)n, (int)nframes, frame0, ctx->Tld, ctx->D, d0, d1, d2);
-    } else {
-        const double* v = (const double*)vsrc;
-        const double* x = (const double*)xsrc;
-        if (hel) k0_stage<double, true><<<grid, block, 0, stream>>>(v, x, masses, series, (int)n, (int)nframes, frame0, ctx->Tld, ctx->D, d0, d1, d2);
-        else k0_stage<double, false><<<grid, block, 0, stream>>>(v, x, masses, series, (int)n, (int)nframes, frame0, ctx->Tld, ctx->D, d0, d1, d2);
-    }
+    const SRC* v = (const SRC*)vsrc;
+    const SRC* x = (const SRC*)xsrc;
+    if (ctx->n_fields == 2) k0_stage<SRC, true, OUT><<<grid, block, 0, stream>>>(v, x, masses, series, (int)n, (int)nframes, frame0, ctx->Tld, ctx->D, d0, d1, d2);
+    else k0_stage<SRC, false, OUT><<<grid, block, 0, stream>>>(v, x, masses, series, (int)n, (int)nframes, frame0, ctx->Tld, ctx->D, d0, d1, d2);
     CK(cudaGetLastError());
     ctx->launches++;
     return TA_OK;
+}
+
+int launch_k0(ta_ctx* ctx, Shard& s, const void* vsrc, const void* xsrc, int64_t a0, int64_t n, int64_t nframes,
+              int64_t frame0, cudaStream_t stream) {
+    const bool f32src = ctx->src_dtype == TA_DTYPE_F32, fp64 = ctx->precision == TA_PRECISION_FP64;
+    if (f32src) return fp64 ? launch_k0_t<float, double>(ctx, s, vsrc, xsrc, a0, n, nframes, frame0, stream)
+                            : launch_k0_t<float, float>(ctx, s, vsrc, xsrc, a0, n, nframes, frame0, stream);
+    return fp64 ? launch_k0_t<double, double>(ctx, s, vsrc, xsrc, a0, n, nframes, frame0, stream)
+                : launch_k0_t<double, float>(ctx, s, vsrc, xsrc, a0, n, nframes, frame0, stream);
 }
 
 // The particle ranges the next K1/K2/K3 call launches over: the staging chunks (each launch waits
@@ -429,76 +424,39 @@ int upload_fft_tables(ta_ctx* ctx, const std::vector<uint32_t>& own0) {
     return TA_OK;
 }
 
+template <typename RT>
 int upload_fast_tables(ta_ctx* ctx, const K1FastPlan& p) {
+    auto conv = [](const std::vector<double>& v) { return std::vector<RT>(v.begin(), v.end()); };
+    const std::vector<RT> omega = conv(p.omega), tw2 = conv(p.tw2), wbase = conv(p.wbase), inv = conv(p.inv);
     for (auto& s : ctx->sh) {
         CK(cudaSetDevice(s.dev));
-        cudaFree(s.f_omega); cudaFree(s.f_tw2); cudaFree(s.f_tw8); cudaFree(s.f_map); cudaFree(s.f_wbase); cudaFree(s.f_inv);
-        s.f_omega = s.f_tw2 = s.f_tw8 = s.f_wbase = nullptr; s.f_map = nullptr; s.f_inv = nullptr;
+        cudaFree(s.f_omega); cudaFree(s.f_tw2); cudaFree(s.f_map); cudaFree(s.f_wbase); cudaFree(s.f_inv);
+        s.f_omega = s.f_tw2 = s.f_wbase = s.f_inv = nullptr; s.f_map = nullptr;
 #define TA_UP(dst, vec)                                                                         \
         CK(cudaMalloc((void**)&dst, vec.size() * sizeof(vec[0])));                              \
         CK(cudaMemcpy(dst, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice));
-        TA_UP(s.f_omega, p.omega);
-        TA_UP(s.f_tw2, p.tw2);
-        TA_UP(s.f_tw8, p.tw8);
+        TA_UP(s.f_omega, omega);
+        TA_UP(s.f_tw2, tw2);
         TA_UP(s.f_map, p.map);
-        TA_UP(s.f_wbase, p.wbase);
-        TA_UP(s.f_inv, p.inv);
+        TA_UP(s.f_wbase, wbase);
+        TA_UP(s.f_inv, inv);
 #undef TA_UP
     }
     return TA_OK;
 }
 
-int upload_r8_tables(ta_ctx* ctx, const K1R8Plan& p) {
-    for (auto& s : ctx->sh) {
-        CK(cudaSetDevice(s.dev));
-        cudaFree(s.e_omega); cudaFree(s.e_tw2); cudaFree(s.e_tw3); cudaFree(s.e_map); cudaFree(s.e_wbase);
-        s.e_omega = s.e_tw2 = s.e_tw3 = s.e_wbase = nullptr; s.e_map = nullptr;
-#define TA_UP(dst, vec)                                                                         \
-        CK(cudaMalloc((void**)&dst, vec.size() * sizeof(vec[0])));                              \
-        CK(cudaMemcpy(dst, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice));
-        TA_UP(s.e_omega, p.omega);
-        TA_UP(s.e_tw2, p.tw2);
-        TA_UP(s.e_tw3, p.tw3);
-        TA_UP(s.e_map, p.map);
-        TA_UP(s.e_wbase, p.wbase);
-#undef TA_UP
-        if (!s.e_slots) CK(cudaMalloc((void**)&s.e_slots, 1024 * sizeof(unsigned)));
-    }
-    return TA_OK;
-}
-
-// Which K1 kernel serves T (FP64): the three-pass radix-16 path where it has an instantiation (the faster of the two
-// wherever both exist: 24.2 against 27.4 ms at 100k x 10k, 23.6 against 25.5 ms at 200k x 5k), else the four-pass radix-8
-// path (T up to 12,288), else the general kernel.  TA_B200_K1_PATH = r16 | r8 | general restricts the choice
-// (experiments and the tests that compare the kernels with each other).
-int plan_r8(ta_ctx* ctx, int r8) {
-    K1R8Plan ep;
-    int rce = k1e_build_plan(ctx->T, r8, &ep);
-    if (rce) return fail(ctx, rce, "cannot plan the radix-8 FFT path for T=" + std::to_string(ctx->T));
-    if ((rce = upload_r8_tables(ctx, ep))) return rce;
-    ctx->fast_r8 = r8;
-    ctx->plan.H = ep.H; ctx->plan.L = ep.L; ctx->plan.npasses = 4;
-    ctx->plan.radix[0] = r8; ctx->plan.radix[1] = 8; ctx->plan.radix[2] = 8; ctx->plan.radix[3] = 8;
-    ctx->plan_T = ctx->T;
-    ctx->plan_prec = ctx->precision;
-    return TA_OK;
-}
-
+// Which K1 kernel serves T: the three-pass radix-16 kernel where it has an instantiation (H = 256 R1 >= T / 2 with at
+// most 34 % padding: T from ~1,540 to 12,288; FP64 and FP32), else the general mixed-radix kernel (any T).
 int ensure_fft_plan(ta_ctx* ctx) {
     if (ctx->plan_T == ctx->T && ctx->plan_prec == ctx->precision) return TA_OK;
     ctx->fast_r1 = 0;
-    ctx->fast_r8 = 0;
-    const char* force_general = getenv("TA_B200_FFT_GENERAL");
-    const char* path = getenv("TA_B200_K1_PATH");
-    const std::string want = (force_general && force_general[0] == '1') ? "general" : (path ? path : "");
     const bool fp64 = ctx->precision == TA_PRECISION_FP64;
-    if (fp64 && want == "r8" && k1e_choose_r(ctx->T) > 0) return plan_r8(ctx, k1e_choose_r(ctx->T));
-    const int r1 = (fp64 && (want.empty() || want == "r16")) ? k1f_choose_r1(ctx->T) : 0;
+    const int r1 = ctx->opt_general_fft ? 0 : k1f_choose_r1(ctx->T);
     if (r1 > 0) {
         K1FastPlan fp;
         int rcf = k1f_build_plan(ctx->T, ctx->Tld, r1, &fp);
         if (rcf) return fail(ctx, rcf, "cannot plan the fast FFT path for T=" + std::to_string(ctx->T));
-        if ((rcf = upload_fast_tables(ctx, fp))) return rcf;
+        if ((rcf = fp64 ? upload_fast_tables<double>(ctx, fp) : upload_fast_tables<float>(ctx, fp))) return rcf;
         ctx->fast_r1 = r1;
         ctx->plan.H = fp.H; ctx->plan.L = fp.L; ctx->plan.npasses = 3;
         ctx->plan.radix[0] = r1; ctx->plan.radix[1] = 16; ctx->plan.radix[2] = 16;
@@ -506,15 +464,13 @@ int ensure_fft_plan(ta_ctx* ctx) {
         ctx->plan_prec = ctx->precision;
         return TA_OK;
     }
-    if (fp64 && want.empty() && k1e_choose_r(ctx->T) > 0) return plan_r8(ctx, k1e_choose_r(ctx->T));
     int rc = ta_build_fft_plan(ctx->T, &ctx->plan);
     if (rc) return fail(ctx, rc, "cannot plan an FFT for T=" + std::to_string(ctx->T));
     std::vector<uint32_t> own0;
     for (int p = 0; p < ctx->plan.H; ++p)
         if ((uint32_t)p <= ctx->plan.pair0[p]) own0.push_back((uint32_t)p);
     ctx->npairs0 = (int)own0.size();
-    rc = (ctx->precision == TA_PRECISION_FP64) ? upload_fft_tables<double>(ctx, own0)
-                                               : upload_fft_tables<float>(ctx, own0);
+    rc = fp64 ? upload_fft_tables<double>(ctx, own0) : upload_fft_tables<float>(ctx, own0);
     if (rc) return rc;
     ctx->plan_T = ctx->T;
     ctx->plan_prec = ctx->precision;
@@ -576,7 +532,7 @@ int launch_fft(ta_ctx* ctx, std::vector<int>* grids) {
         CK(cudaEventRecord(s.ev_ka, s.s_compute));
         for (const LaunchRange& rg : take_launch_ranges(s)) {
             if (rg.ready) CK(cudaStreamWaitEvent(s.s_compute, rg.ready, 0));
-            a.series = s.series + (size_t)rg.a0 * ctx->D * ctx->Tld;
+            a.series = (const R*)s.series + (size_t)rg.a0 * ctx->D * ctx->Tld;
             a.by_particle = s.by_particle + (size_t)rg.a0 * ctx->Tld;
             a.natoms = (int)rg.n;
             kern<<<(int)std::min<int64_t>(grid, rg.n), nthr, dyn, s.s_compute>>>(a);
@@ -590,189 +546,75 @@ int launch_fft(ta_ctx* ctx, std::vector<int>* grids) {
     return TA_OK;
 }
 
-int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return (v && v[0]) ? atoi(v) : dflt;
-}
-
-template <int R1, int NT, bool PROF = false, int VAR = 0>
-int launch_fft_fast_r1(ta_ctx* ctx, std::vector<int>* grids, void (*kern)(const K1FArgs) = k1f_fft_acf<R1, NT, PROF, VAR>) {
-    const int smem = k1f_smem_bytes(R1, VAR);
-    const int nthr = NT;
-    grids->assign(ctx->sh.size(), 0);
-    for (size_t i = 0; i < ctx->sh.size(); ++i) {
-        Shard& s = ctx->sh[i];
-        if (s.natoms == 0) continue;
-        CK(cudaSetDevice(s.dev));
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nthr, (size_t)smem));
-        if (occ < 1) return fail(ctx, TA_ERR_UNSUPPORTED, "fast FFT kernel does not fit on an SM");
-        int grid = (int)std::min<int64_t>(s.natoms, (int64_t)s.num_sms * occ);
-        (*grids)[i] = grid;
-        int rc = ensure_partial(ctx, s, (size_t)grid);
-        if (rc) return rc;
-        K1FArgs a;
-        a.partial = s.partial;
-        a.omega = (const cd*)s.f_omega; a.tw2 = (const cd*)s.f_tw2; a.tw8 = (const cd*)s.f_tw8; a.map = s.f_map;
-        a.wbase = (const cd*)s.f_wbase; a.inv = s.f_inv;
-        a.D = ctx->D; a.T = (int)ctx->T; a.nh = (int)((ctx->T + 1) / 2); a.Tld = ctx->Tld;
-        a.prefetch = env_int("TA_B200_K1F_PREFETCH", 0);
-        a.stagger = env_int("TA_B200_K1F_STAGGER", 0);
-        a.prof = nullptr;
-        const bool profile = PROF;   // debug instantiation: per-phase clocks of thread 0 to stderr
-        if (profile) {
-            CK(cudaMalloc((void**)&a.prof, (size_t)grid * 32 * sizeof(long long)));
-            CK(cudaMemsetAsync(a.prof, 0, (size_t)grid * 32 * sizeof(long long), s.s_compute));
-        }
-        CK(cudaEventRecord(s.ev_ka, s.s_compute));
-        for (const LaunchRange& rg : take_launch_ranges(s)) {
-            if (rg.ready) CK(cudaStreamWaitEvent(s.s_compute, rg.ready, 0));
-            a.series = s.series + (size_t)rg.a0 * ctx->D * ctx->Tld;
-            a.by_particle = s.by_particle + (size_t)rg.a0 * ctx->Tld;
-            a.natoms = (int)rg.n;
-            kern<<<(int)std::min<int64_t>(grid, rg.n), nthr, smem, s.s_compute>>>(a);
-            CK(cudaGetLastError());
-            ctx->launches++;
-        }
-        CK(cudaEventRecord(s.ev_kb, s.s_compute));
-        if (profile) {
-            std::vector<long long> h((size_t)grid * 32);
-            CK(cudaStreamSynchronize(s.s_compute));
-            CK(cudaMemcpy(h.data(), a.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-            CK(cudaFree(a.prof));
-            double tot[32] = {0}, all = 0;
-            for (int b = 0; b < grid; ++b) for (int q = 0; q < 32; ++q) { tot[q] += (double)h[(size_t)b * 32 + q]; all += (double)h[(size_t)b * 32 + q]; }
-            const char* nm[16] = {"P1.ld", "P1.fp", "P1.st+bar", "P2.ld", "P2.fp", "P2.st+bar", "P3.ld", "P3.fp", "P3.bar",
-                                  "P3i.fp", "P3i.st+bar", "P2i.ld+fp", "P2i.st+bar", "P1i.ld+fp", "out", "-"};
-            const double atoms_per_cta = (double)s.natoms / grid;
-            fprintf(stderr, "[k1f profile] R1=%d NT=%d grid=%d clocks/CTA=%.0f clocks/atom=%.0f\n", R1, NT, grid, all / grid,
-                    all / grid / atoms_per_cta);
-            for (int q = 0; q < 32; ++q)
-                if (tot[q] > 0) fprintf(stderr, "   r%d.%-11s %5.1f%%  %7.0f clk/atom\n", q / 16, nm[q % 16], 100.0 * tot[q] / all,
-                                        tot[q] / grid / atoms_per_cta);
-        }
-        s.kernel_timed = true;
-        ctx->k1_threads = nthr; ctx->k1_smem = smem; ctx->k1_grid = grid;
-    }
-    return TA_OK;
-}
-
-template <int R>
-int launch_fft_r8_r(ta_ctx* ctx, std::vector<int>* grids) {
-    // TA_B200_K1E_ONE_CTA=1 (experiments): pad the shared memory request so that only one CTA fits on an SM
-    const int smem = env_int("TA_B200_K1E_ONE_CTA", 0) ? std::max(k1e_smem_bytes(R), 120 * 1024) : k1e_smem_bytes(R);
-    const int nthr = k1e_threads(R);
-    grids->assign(ctx->sh.size(), 0);
-    for (size_t i = 0; i < ctx->sh.size(); ++i) {
-        Shard& s = ctx->sh[i];
-        if (s.natoms == 0) continue;
-        CK(cudaSetDevice(s.dev));
-        if (smem > s.max_smem) return fail(ctx, TA_ERR_UNSUPPORTED, "radix-8 FFT kernel needs more shared memory than the device has");
-        CK(cudaFuncSetAttribute(k1e_fft_acf<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1e_fft_acf<R>, nthr, (size_t)smem));
-        if (occ < 1) return fail(ctx, TA_ERR_UNSUPPORTED, "radix-8 FFT kernel does not fit on an SM");
-        int grid = (int)std::min<int64_t>(s.natoms, (int64_t)s.num_sms * occ);
-        (*grids)[i] = grid;
-        int rc = ensure_partial(ctx, s, (size_t)grid);
-        if (rc) return rc;
-        K1EArgs a;
-        a.partial = s.partial;
-        a.omega = (const cd*)s.e_omega; a.tw2 = (const cd*)s.e_tw2; a.tw3 = (const cd*)s.e_tw3;
-        a.map = s.e_map; a.wbase = (const cd*)s.e_wbase;
-        a.D = ctx->D; a.T = (int)ctx->T; a.nh = (int)((ctx->T + 1) / 2); a.Tld = ctx->Tld;
-        a.sm_slots = s.e_slots;
-        a.stagger = occ >= 2 ? env_int("TA_B200_K1E_STAGGER", 0) : 0;
-        CK(cudaEventRecord(s.ev_ka, s.s_compute));
-        for (const LaunchRange& rg : take_launch_ranges(s)) {
-            if (rg.ready) CK(cudaStreamWaitEvent(s.s_compute, rg.ready, 0));
-            a.series = s.series + (size_t)rg.a0 * ctx->D * ctx->Tld;
-            a.by_particle = s.by_particle + (size_t)rg.a0 * ctx->Tld;
-            a.natoms = (int)rg.n;
-            if (a.stagger > 0) CK(cudaMemsetAsync(s.e_slots, 0, 1024 * sizeof(unsigned), s.s_compute));
-            k1e_fft_acf<R><<<(int)std::min<int64_t>(grid, rg.n), nthr, smem, s.s_compute>>>(a);
-            CK(cudaGetLastError());
-            ctx->launches++;
-        }
-        CK(cudaEventRecord(s.ev_kb, s.s_compute));
-        s.kernel_timed = true;
-        ctx->k1_threads = nthr; ctx->k1_smem = smem; ctx->k1_grid = grid;
-    }
-    return TA_OK;
-}
-
-int launch_fft_r8(ta_ctx* ctx, std::vector<int>* grids) {
-    switch (ctx->fast_r8) {
-        case 4: return launch_fft_r8_r<4>(ctx, grids);
-        case 5: return launch_fft_r8_r<5>(ctx, grids);
-        case 6: return launch_fft_r8_r<6>(ctx, grids);
-        case 8: return launch_fft_r8_r<8>(ctx, grids);
-        case 10: return launch_fft_r8_r<10>(ctx, grids);
-        case 12: return launch_fft_r8_r<12>(ctx, grids);
-    }
-    return fail(ctx, TA_ERR_UNSUPPORTED, "no radix-8 FFT instantiation for R=" + std::to_string(ctx->fast_r8));
-}
-
-// k1_fast.cuh VAR bits served per R1: 0 and 4 (bulk series prefetch) everywhere, the other experiments at R1 = 20.
-// Default: prefetch on where its buffer does not cost a resident CTA (R1 >= 8; measured 25.4 -> 24.2 ms at 100k x 10k,
-// 25.1 -> 23.6 ms at 200k x 5k), off at R1 = 4 and 6 (six -> five and four -> three CTAs per SM: 6.15 -> 6.21 ms at
-// 150k x 2,000, 6.41 -> 6.87 ms at 100k x 3,000); TA_B200_K1F_VAR overrides.
-template <int R1>
-int launch_fft_fast_var(ta_ctx* ctx, std::vector<int>* grids) {
-    const int var = env_int("TA_B200_K1F_VAR", R1 >= 8 ? K1F_VAR_PREFETCH : 0);
+template <int R1, typename RT>
+int launch_fft_fast_r1(ta_ctx* ctx, std::vector<int>* grids) {
     constexpr int NT = k1f_threads(R1);
-    if (var == 0) return launch_fft_fast_r1<R1, NT, false, 0>(ctx, grids);
-    if (var == 4) {
-        // ten warps per SM: register cap stated with __maxnreg__ (kernels.cuh); TA_B200_K1F_MAXREG=0 keeps the launch bounds
-        if constexpr (NT == 320)
-            if (env_int("TA_B200_K1F_MAXREG", K1F_MAXREG) == K1F_MAXREG) {
-                // the cap is above what fits (170); should a compiler settle higher than the 166 it uses today, the
-                // launch-bounds build of the same kernel takes over
-                int occ = 0;
-                cudaFuncSetAttribute(k1f_fft_acf_mr<R1, NT, 4, K1F_MAXREG>, cudaFuncAttributeMaxDynamicSharedMemorySize, k1f_smem_bytes(R1, 4));
-                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1f_fft_acf_mr<R1, NT, 4, K1F_MAXREG>, NT,
-                                                                  (size_t)k1f_smem_bytes(R1, 4)) == cudaSuccess && occ >= 1)
-                    return launch_fft_fast_r1<R1, NT, false, 4>(ctx, grids, k1f_fft_acf_mr<R1, NT, 4, K1F_MAXREG>);
-                cudaGetLastError();
-            }
-        return launch_fft_fast_r1<R1, NT, false, 4>(ctx, grids);
+    const int smem = k1f_smem_bytes(R1, k1f_prefetch(R1, (int)sizeof(RT)), (int)sizeof(RT));
+    grids->assign(ctx->sh.size(), 0);
+    for (size_t i = 0; i < ctx->sh.size(); ++i) {
+        Shard& s = ctx->sh[i];
+        if (s.natoms == 0) continue;
+        CK(cudaSetDevice(s.dev));
+        void (*kern)(const K1FArgs<RT>) = k1f_fft_acf<R1, RT>;
+        if (smem > s.max_smem) return fail(ctx, TA_ERR_UNSUPPORTED, "three-pass FFT kernel needs more shared memory than the device has");
+        int occ = 0;
+        if constexpr (NT == 320 && sizeof(RT) == 8) {
+            // ten FP64 warps per SM: the build with the register cap stated outright (kernels.cuh); should a compiler
+            // settle above what fits, the launch-bounds build of the same kernel takes over
+            cudaFuncSetAttribute(k1f_fft_acf_mr<R1, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1f_fft_acf_mr<R1, RT>, NT, (size_t)smem) == cudaSuccess && occ >= 1)
+                kern = k1f_fft_acf_mr<R1, RT>;
+            else cudaGetLastError();
+        }
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, (size_t)smem));
+        if (occ < 1) return fail(ctx, TA_ERR_UNSUPPORTED, "three-pass FFT kernel does not fit on an SM");
+        int grid = (int)std::min<int64_t>(s.natoms, (int64_t)s.num_sms * occ);
+        (*grids)[i] = grid;
+        int rc = ensure_partial(ctx, s, (size_t)grid);
+        if (rc) return rc;
+        K1FArgs<RT> a;
+        a.partial = s.partial;
+        a.omega = (const cplx<RT>*)s.f_omega; a.tw2 = (const cplx<RT>*)s.f_tw2; a.map = s.f_map;
+        a.wbase = (const cplx<RT>*)s.f_wbase; a.inv = (const RT*)s.f_inv;
+        a.D = ctx->D; a.T = (int)ctx->T; a.nh = (int)((ctx->T + 1) / 2); a.Tld = ctx->Tld;
+        CK(cudaEventRecord(s.ev_ka, s.s_compute));
+        for (const LaunchRange& rg : take_launch_ranges(s)) {
+            if (rg.ready) CK(cudaStreamWaitEvent(s.s_compute, rg.ready, 0));
+            a.series = (const RT*)s.series + (size_t)rg.a0 * ctx->D * ctx->Tld;
+            a.by_particle = s.by_particle + (size_t)rg.a0 * ctx->Tld;
+            a.natoms = (int)rg.n;
+            kern<<<(int)std::min<int64_t>(grid, rg.n), NT, smem, s.s_compute>>>(a);
+            CK(cudaGetLastError());
+            ctx->launches++;
+        }
+        CK(cudaEventRecord(s.ev_kb, s.s_compute));
+        s.kernel_timed = true;
+        ctx->k1_threads = NT; ctx->k1_smem = smem; ctx->k1_grid = grid;
     }
-    if (var == 12) return launch_fft_fast_r1<R1, NT, false, 12>(ctx, grids);
-    if constexpr (R1 == 20) {
-        if (var == 1) return launch_fft_fast_r1<20, k1f_threads(20), false, 1>(ctx, grids);
-        if (var == 2) return launch_fft_fast_r1<20, k1f_threads(20), false, 2>(ctx, grids);
-        if (var == 3) return launch_fft_fast_r1<20, k1f_threads(20), false, 3>(ctx, grids);
-        if (var == 5) return launch_fft_fast_r1<20, k1f_threads(20), false, 5>(ctx, grids);
-        if (var == 8) return launch_fft_fast_r1<20, k1f_threads(20), false, 8>(ctx, grids);
-    }
-    return fail(ctx, TA_ERR_UNSUPPORTED, "no instantiation of the three-pass FFT kernel for TA_B200_K1F_VAR=" + std::to_string(var));
+    return TA_OK;
 }
 
+template <typename RT>
 int launch_fft_fast(ta_ctx* ctx, std::vector<int>* grids) {
-    if (ctx->fast_r8 > 0) return launch_fft_r8(ctx, grids);
     switch (ctx->fast_r1) {
-        case 4: return launch_fft_fast_var<4>(ctx, grids);
-        case 6: return launch_fft_fast_var<6>(ctx, grids);
-        case 8: return launch_fft_fast_var<8>(ctx, grids);
-        case 10: return launch_fft_fast_var<10>(ctx, grids);
-        case 12: return launch_fft_fast_var<12>(ctx, grids);
-        case 16: return launch_fft_fast_var<16>(ctx, grids);
-        case 20: {
-            if (env_int("TA_B200_K1F_PROFILE", 0)) return launch_fft_fast_r1<20, k1f_threads(20), true>(ctx, grids);
-            const int nt = env_int("TA_B200_K1F_NT", k1f_threads(20));   // experiments: two CTAs per SM
-            // few fat warps: one (two) per sub-partition, 255 registers, several butterflies per thread and pass
-            if (nt == 128) return launch_fft_fast_r1<20, 128, false, 4>(ctx, grids, k1f_fft_acf_mr<20, 128, 4, 255>);
-            if (nt == 256) return launch_fft_fast_r1<20, 256, false, 4>(ctx, grids, k1f_fft_acf_mr<20, 256, 4, 255>);
-            if (nt == 192) return launch_fft_fast_r1<20, 192>(ctx, grids);
-            if (nt == 160) return launch_fft_fast_r1<20, 160>(ctx, grids);
-            const int mr = env_int("TA_B200_K1F_MAXREG", K1F_MAXREG);      // experiments: other explicit register caps
-            if (mr == 160) return launch_fft_fast_r1<20, 320, false, 4>(ctx, grids, k1f_fft_acf_mr<20, 320, 4, 160>);
-            if (mr == 168) return launch_fft_fast_r1<20, 320, false, 4>(ctx, grids, k1f_fft_acf_mr<20, 320, 4, 168>);
-            return launch_fft_fast_var<20>(ctx, grids);
-        }
+        case 4: return launch_fft_fast_r1<4, RT>(ctx, grids);
+        case 6: return launch_fft_fast_r1<6, RT>(ctx, grids);
+        case 8: return launch_fft_fast_r1<8, RT>(ctx, grids);
+        case 10: return launch_fft_fast_r1<10, RT>(ctx, grids);
+        case 12: return launch_fft_fast_r1<12, RT>(ctx, grids);
+        case 16: return launch_fft_fast_r1<16, RT>(ctx, grids);
+        case 20: return launch_fft_fast_r1<20, RT>(ctx, grids);
+        case 24: return launch_fft_fast_r1<24, RT>(ctx, grids);
     }
     return fail(ctx, TA_ERR_UNSUPPORTED, "no fast FFT instantiation for R1=" + std::to_string(ctx->fast_r1));
+}
+
+// the FFT autocorrelation pass of ta_vacf_fft / ta_helfand_fft: by_particle = sum_d acf_d, per-CTA partial rows
+int launch_k1(ta_ctx* ctx, std::vector<int>* grids) {
+    const bool fp64 = ctx->precision == TA_PRECISION_FP64;
+    if (ctx->fast_r1 > 0) return fp64 ? launch_fft_fast<double>(ctx, grids) : launch_fft_fast<float>(ctx, grids);
+    return fp64 ? launch_fft<double>(ctx, grids) : launch_fft<float>(ctx, grids);
 }
 
 template <typename R, int MODE>
@@ -817,7 +659,7 @@ int launch_windowed(ta_ctx* ctx, double denom, std::vector<int>* grids) {
         CK(cudaEventRecord(s.ev_ka, s.s_compute));
         for (const LaunchRange& rg : take_launch_ranges(s)) {
             if (rg.ready) CK(cudaStreamWaitEvent(s.s_compute, rg.ready, 0));
-            a.series = s.series + (size_t)rg.a0 * ctx->D * ctx->Tld;
+            a.series = (const R*)s.series + (size_t)rg.a0 * ctx->D * ctx->Tld;
             a.by_particle = s.by_particle + (size_t)rg.a0 * ctx->Tld;
             a.natoms = (int)rg.n;
             if (in_smem) k_windowed<R, MODE, false><<<(int)std::min<int64_t>(grid, rg.n), nthr, dyn_smem, s.s_compute>>>(a);
@@ -839,6 +681,10 @@ int create_common(ta_ctx* ctx, int ndev, const int* devices) {
                     std::string("no CUDA device available (") + cudaGetErrorString(e) +
                         "); libta_b200 has no CPU fallback");
     if (ndev < 1) return fail(ctx, TA_ERR_INVALID, "ndev must be >= 1");
+    // debugging knobs (see ta_ctx): read here, once, never on a launch path
+    if (const char* v = getenv("TA_B200_K1_PATH")) ctx->opt_general_fft = std::string(v) == "general";
+    if (const char* v = getenv("TA_B200_BULK_CHUNK")) ctx->opt_bulk_chunk = atoll(v);
+    if (const char* v = getenv("TA_B200_HELFAND_FFT_THR")) ctx->opt_helfand_thr = atof(v);
     ctx->sh.resize(ndev);
     for (int i = 0; i < ndev; ++i) {
         int dev = devices ? devices[i] : i;
@@ -992,7 +838,7 @@ int ta_stage_begin(ta_ctx* ctx, int64_t T, int64_t N, int D, const int* dims, in
     if (n_fields == 2 && !masses && N > 0) return fail(ctx, TA_ERR_INVALID, "masses are required with n_fields == 2");
     if (precision != TA_PRECISION_FP64 && precision != TA_PRECISION_FP32) return fail(ctx, TA_ERR_INVALID, "bad precision");
     if (ctx->begun && ctx->T == T && ctx->N == N && ctx->D == D && ctx->src_dtype == src_dtype &&
-        ctx->n_fields == n_fields) {
+        ctx->n_fields == n_fields && ctx->precision == precision) {
         // same shape as the previous run on this context: keep every buffer
         // (the pad region of the series is never written, so it is still zero)
         int rc0 = sync_all(ctx);
@@ -1036,7 +882,8 @@ int ta_stage_begin(ta_ctx* ctx, int64_t T, int64_t N, int D, const int* dims, in
         CK(cudaSetDevice(s.dev));
         CK(cudaMalloc(&s.ts_sum, ((size_t)ctx->Tld + 16) * sizeof(double)));
         if (s.natoms == 0) continue;
-        const size_t ser_bytes = (size_t)s.natoms * D * ctx->Tld * sizeof(double);
+        // the series are stored in the arithmetic type: double, or float in the FP32 mode
+        const size_t ser_bytes = (size_t)s.natoms * D * ctx->Tld * (precision == TA_PRECISION_FP64 ? sizeof(double) : sizeof(float));
         const size_t out_bytes = (size_t)s.natoms * ctx->Tld * sizeof(double);
         cudaError_t e = cudaMalloc(&s.series, ser_bytes);
         if (e == cudaSuccess) e = cudaMalloc(&s.by_particle, out_bytes);
@@ -1115,7 +962,7 @@ int ta_stage_bulk(ta_ctx* ctx, const void* const* fields, int64_t src_atoms, int
     // correlation kernel of a chunk can start as soon as the chunk has landed: ~256 MB per chunk and
     // field, a multiple of 296 particles (two resident CTAs on each of the 148 SMs).
     const int64_t want = std::max<int64_t>(1, ((int64_t)256 << 20) / (T * 3 * (int64_t)ctx->elt));
-    const int64_t env_chunk = env_int("TA_B200_BULK_CHUNK", 0);
+    const int64_t env_chunk = ctx->opt_bulk_chunk;
     for (auto& s : ctx->sh) {
         if (s.natoms == 0) continue;
         CK(cudaSetDevice(s.dev));
@@ -1180,9 +1027,7 @@ int ta_vacf_fft(ta_ctx* ctx, double* ts_out) {
     if (!ts_out) return fail(ctx, TA_ERR_INVALID, "ts_out is null");
     if ((rc = ensure_fft_plan(ctx))) return rc;
     std::vector<int> grids;
-    if (ctx->fast_r1 > 0 || ctx->fast_r8 > 0) rc = launch_fft_fast(ctx, &grids);
-    else rc = (ctx->precision == TA_PRECISION_FP64) ? launch_fft<double>(ctx, &grids) : launch_fft<float>(ctx, &grids);
-    if (rc) return rc;
+    if ((rc = launch_k1(ctx, &grids))) return rc;
     return finish_timeseries(ctx, grids, ts_out);
 }
 
@@ -1222,17 +1067,21 @@ int ta_helfand_fft(ta_ctx* ctx, const double* volumes, double boltzmann, double 
     double vsum = 0.0;
     for (int64_t i = 0; i < ctx->T; ++i) vsum += volumes[i];
     const double denom = 2 * boltzmann * (vsum / (double)ctx->T) * temp_avg;   // viscosity.py:205, :229-231
+    // K5 / K6 keep T + 1 prefix sums in shared memory: refuse BEFORE the FFT pass runs, so that a caller that falls
+    // back to ta_helfand has not paid for it
+    for (auto& s : ctx->sh)
+        if (s.natoms > 0 && ((size_t)ctx->T + 1) * sizeof(double) > (size_t)s.max_smem)
+            return fail(ctx, TA_ERR_UNSUPPORTED, "FFT Helfand route: T=" + std::to_string(ctx->T) + " does not fit shared memory");
     if ((rc = ensure_fft_plan(ctx))) return rc;
     std::vector<int> grids;
-    rc = (ctx->fast_r1 > 0 || ctx->fast_r8 > 0) ? launch_fft_fast(ctx, &grids) : launch_fft<double>(ctx, &grids);   // by_particle = sum_d acf_d
-    if (rc) return rc;
+    if ((rc = launch_k1(ctx, &grids))) return rc;                 // by_particle = sum_d acf_d
     // K5 forms S1 - 2 S2 and marks the lags whose result is not good to 1e-10 (cancellation); K6 evaluates those exactly and
     // sums the particles.  thr = C eps / tol: C = 100 + T / 100 bounds the error constant of S1 - 2 S2 (FFT autocorrelation +
     // prefix sums; measured 11 - 18 on random, random-walk and ramp moments, 15 at T = 3,000 and 33 at T = 10,000 on smooth
     // ones: scripts/helfand_fft_error_constant.py), tol = 2e-11 leaves a factor 5 to the 1e-10 bar on top of that.
     // If a shard has more than 2 % of its (particle, lag) pairs marked, the direct kernel K3 does that shard instead.
-    const char* thr_env = getenv("TA_B200_HELFAND_FFT_THR");
-    const double thr = thr_env ? atof(thr_env) : (100.0 + (double)ctx->T / 100.0) * 1.1102230246251565e-16 / 2e-11;
+    const double thr = ctx->opt_helfand_thr >= -1.5 ? ctx->opt_helfand_thr
+                                                    : (100.0 + (double)ctx->T / 100.0) * 1.1102230246251565e-16 / 2e-11;
     const size_t smem = ((size_t)ctx->T + 1) * sizeof(double);
     const int nwords = (int)((ctx->T + 31) / 32);
     std::vector<unsigned long long> nflag(ctx->sh.size(), 0);
@@ -1265,7 +1114,7 @@ int ta_helfand_fft(ta_ctx* ctx, const double* volumes, double boltzmann, double 
         grids[i] = grid;
         if ((rc = ensure_partial(ctx, s, (size_t)grid))) return rc;    // drops K1's partial rows (sums of the ACF)
         HelfandFftArgs a;
-        a.series = s.series; a.by_particle = s.by_particle; a.partial = s.partial;
+        a.series = (const double*)s.series; a.by_particle = s.by_particle; a.partial = s.partial;
         a.natoms = (int)s.natoms; a.D = ctx->D; a.T = (int)ctx->T; a.Tld = ctx->Tld; a.denom = denom;
         a.flags = s.hflags; a.nwords = nwords; a.nflagged = counter; a.thr = thr;
         k5_helfand_fft_finish<<<grid, K5_THREADS, smem, s.s_compute>>>(a);
@@ -1297,7 +1146,7 @@ int ta_helfand_fft(ta_ctx* ctx, const double* volumes, double boltzmann, double 
         if (nflag[i] == 0) continue;                                  // nothing to correct on this shard
         const int grid = grids[i];
         HelfandFftArgs a;
-        a.series = s.series; a.by_particle = s.by_particle; a.partial = s.partial;
+        a.series = (const double*)s.series; a.by_particle = s.by_particle; a.partial = s.partial;
         a.natoms = (int)s.natoms; a.D = ctx->D; a.T = (int)ctx->T; a.Tld = ctx->Tld; a.denom = denom;
         a.flags = s.hflags; a.nwords = nwords; a.nflagged = nullptr; a.thr = thr;
         k6_helfand_refine<<<grid, K5_THREADS, smem, s.s_compute>>>(a);

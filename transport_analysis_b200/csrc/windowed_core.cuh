@@ -137,7 +137,7 @@ TA_HD double win_reduce16(const R* acc, bool take, int lane) {
 }
 
 struct WinArgs {
-    const double* series;   // [natoms][D][Tld]
+    const void* series;     // [natoms][D][Tld] of the arithmetic type R (double, or float in the FP32 mode)
     double* by_particle;    // [natoms][Tld]
     double* partial;        // [nblk][Tld]
     int natoms, D, T;
@@ -169,11 +169,11 @@ TA_HD void win_body(const WinArgs& A, unsigned char* smem_raw, int tid, int nthr
     for (int a = bid; a < A.natoms; a += nblk) {
         for (int k = tid; k < T; k += nthr) res[k] = 0.0;
         for (int d = 0; d < A.D; ++d) {
-            const double* ser = A.series + ((size_t)a * A.D + d) * A.Tld;
+            const R* ser = reinterpret_cast<const R*>(A.series) + ((size_t)a * A.D + d) * A.Tld;
             Ctx::sync();   // previous series fully consumed
             for (int x = tid; x < ne; x += nthr) S[x] = (R)0;
             Ctx::sync();
-            for (int x = tid; x < T; x += nthr) S[win_addr(x)] = (R)ser[x];
+            for (int x = tid; x < T; x += nthr) S[win_addr(x)] = ser[x];
             Ctx::sync();
             // ---- unmasked tiles: a warp per block pair, lanes split between the two blocks
             for (int pair = warp; pair < npairs; pair += nwarps) {

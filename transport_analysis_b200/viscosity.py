@@ -7,10 +7,11 @@ step)``, ``results.timeseries`` / ``results.visc_by_particle`` /
 ``results.viscosity``.  Velocities and positions are staged together; the
 Helfand moment ``g = (m*v)*x`` is formed on the device while staging (kernel
 K0) and ``_conclude`` is one call into ``libta_b200.so``: the mean-squared
-displacement of ``g`` as ``S1 - 2 S2`` with the FFT autocorrelation kernel and
-an exact re-evaluation of every lag where that difference is not good to 1e-10
-(kernels K1 + K5 + K6), or the direct windowed sums (kernel K3).  There is no
-CPU fallback.
+displacement of ``g`` by the reference's own direct lag sums (kernel K3, the
+default) or, opt-in with ``fft=True``, as ``S1 - 2 S2`` with the FFT
+autocorrelation kernel and an exact re-evaluation of every lag where that
+difference is not good to 1e-10 (kernels K1 + K5 + K6).  There is no CPU
+fallback.
 """
 from __future__ import annotations
 
@@ -36,18 +37,20 @@ class ViscosityHelfand(AnalysisBase):
     Extra keyword arguments: ``precision``, ``devices``, ``max_eager_bytes``
     as for :class:`~transport_analysis_b200.velocityautocorr.VelocityAutocorr`, and
 
-    ``fft``  ``"auto"`` (default): the O(T log T) route where it applies (FP64, T <~ 29,000), else the direct sums.
+    ``fft``  ``False`` (default): the direct O(T^2) lag sums of the reference for every lag (viscosity.py:210-226).
              ``True``: the O(T log T) route ``sum (g_i - g_{i+k})^2 = S1[k] - 2 S2[k]`` with ``S2`` from the FFT
              autocorrelation kernel -- the idea the reference's dev notebook leaves for later
              (docs/tutorials/helfand_dev_toy_system.ipynb:134).  The difference cancels (relative error about
              ``30 eps sum(g^2) / MSD[k]``: 1e-9 at the short lags of smooth moments), so every lag whose MSD is below
              ``thr * sum(g^2)`` is re-evaluated with the exact sum of the reference (viscosity.py:212-226); if more than
-             2 % of a shard's lags need that, the direct kernel does the shard.  Meets the same 1e-10 bar as
-             ``False``: the direct O(T^2) lag sums of the reference for every lag.
+             2 % of a shard's lags need that, the direct kernel does the shard.  Meets the same 1e-10 bar as the
+             default on every trajectory family of tests/test_gpu_parity.py, but it is a different summation, hence
+             opt-in.
+             ``"auto"``: ``True`` where the O(T log T) route applies (FP64, T <= ~29,000), else the direct sums.
     """
 
     def __init__(self, atomgroup, temp_avg=300.0, dim_type="xyz", linear_fit_window=None,
-                 precision="fp64", devices=None, max_eager_bytes=1 << 26, fft="auto", **kwargs):
+                 precision="fp64", devices=None, max_eager_bytes=1 << 26, fft=False, **kwargs):
         super().__init__(atomgroup.universe.trajectory, **kwargs)
 
         if isinstance(atomgroup, UpdatingAtomGroup):
