@@ -123,10 +123,16 @@ int ta_fetch_by_particle(ta_ctx* ctx, int64_t atom0, int64_t natoms, int layout,
  * events on every shard's compute stream; ms = max over local devices). */
 int ta_timer_begin(ta_ctx* ctx);
 int ta_timer_end(ta_ctx* ctx, float* ms);
-/* Device time of the dominant kernel (K1, K2 or K3) of the last compute call,
- * from CUDA events recorded around that launch on its own stream (max over
- * local devices). */
+/* Device time of the kernels of the last compute call that do the correlation work -- K1, K2 or K3; K1 + K5 + K6 for
+ * ta_helfand_fft -- from CUDA events recorded around those launches on their own stream (max over local devices). */
 int ta_last_kernel_ms(ta_ctx* ctx, float* ms);
+/* Probes for the roofline denominators bench.py reports beside MEASURED_PEAKS.json (which holds HBM and bf16 only):
+ * ta_probe_fp64: FP64 FMA rate of the context's first device, TFLOP/s (independent DFMA chains on every SM, CUDA
+ * events on the compute stream).  ta_probe_h2d: rate of one contiguous `bytes`-long cudaMemcpyAsync from pinned host
+ * memory to the context's first device, GB/s (the ceiling the staging copies of ta_stage_bulk are measured against;
+ * call it on all ranks at once to see the box's concurrent ceiling). */
+int ta_probe_fp64(ta_ctx* ctx, double* tflops);
+int ta_probe_h2d(ta_ctx* ctx, uint64_t bytes, double* gbps);
 /* Overwrite a 512 MB scratch buffer so that nothing of the inputs stays in L2
  * (benchmark hygiene for workloads smaller than the 126 MB L2). */
 int ta_flush_l2(ta_ctx* ctx);

@@ -44,6 +44,8 @@ _SIGNATURES = {
     "ta_timer_begin": (c_int, [c_void_p]),
     "ta_timer_end": (c_int, [c_void_p, POINTER(c_float)]),
     "ta_last_kernel_ms": (c_int, [c_void_p, POINTER(c_float)]),
+    "ta_probe_fp64": (c_int, [c_void_p, POINTER(c_double)]),
+    "ta_probe_h2d": (c_int, [c_void_p, c_uint64, POINTER(c_double)]),
     "ta_flush_l2": (c_int, [c_void_p]),
     "ta_launch_count": (c_int64, [c_void_p]),
     "ta_helfand_fft_refined": (c_int64, [c_void_p]),
@@ -128,6 +130,7 @@ class Context:
         self.T = self.N = 0
         self._n_fields = 1
         self._np_dtype = np.float32
+        self._keepalive = None
 
     # -- plumbing ---------------------------------------------------------
     def _check(self, rc: int, what: str):
@@ -208,11 +211,13 @@ class Context:
     def vacf_fft(self) -> np.ndarray:
         ts = np.empty(self.T, dtype=np.float64)
         self._check(self._lib.ta_vacf_fft(self._h, _dptr(ts)), "ta_vacf_fft")
+        self._keepalive = None            # the call has waited for every staging copy
         return ts
 
     def vacf_windowed(self) -> np.ndarray:
         ts = np.empty(self.T, dtype=np.float64)
         self._check(self._lib.ta_vacf_windowed(self._h, _dptr(ts)), "ta_vacf_windowed")
+        self._keepalive = None
         return ts
 
     def helfand(self, volumes, boltzmann: float, temp_avg: float, fft: bool = False) -> np.ndarray:
@@ -224,6 +229,7 @@ class Context:
         ts = np.empty(self.T, dtype=np.float64)
         fn, name = (self._lib.ta_helfand_fft, "ta_helfand_fft") if fft else (self._lib.ta_helfand, "ta_helfand")
         self._check(fn(self._h, _dptr(vol), float(boltzmann), float(temp_avg), _dptr(ts)), name)
+        self._keepalive = None
         return ts
 
     def fetch_by_particle(self, atom0=0, natoms=None, lag_major_copy=False) -> np.ndarray:
@@ -256,6 +262,18 @@ class Context:
         self._check(self._lib.ta_last_kernel_ms(self._h, ctypes.byref(ms)), "ta_last_kernel_ms")
         return float(ms.value)
 
+    def probe_fp64(self) -> float:
+        """Measured FP64 FMA rate of the first device of this context, TFLOP/s."""
+        v = c_double()
+        self._check(self._lib.ta_probe_fp64(self._h, ctypes.byref(v)), "ta_probe_fp64")
+        return float(v.value)
+
+    def probe_h2d(self, nbytes: int = 1 << 30) -> float:
+        """Rate of a contiguous pinned host -> device copy on the first device of this context, GB/s."""
+        v = c_double()
+        self._check(self._lib.ta_probe_h2d(self._h, c_uint64(int(nbytes)), ctypes.byref(v)), "ta_probe_h2d")
+        return float(v.value)
+
     def flush_l2(self):
         self._check(self._lib.ta_flush_l2(self._h), "ta_flush_l2")
 
@@ -285,3 +303,43 @@ def host_register(arr: np.ndarray):
 def host_unregister(arr: np.ndarray):
     lib = load_library()
     lib.ta_host_unregister(c_void_p(arr.ctypes.data))
+
+
+# Page-locked registrations made on behalf of the analysis classes (FrameStager.try_bulk): one per array, keyed by
+# address, dropped when the array is garbage-collected.  Arrays the caller registered itself are left alone.
+_PINNED: dict = {}
+
+
+def is_pinned(arr: np.ndarray) -> bool:
+    ent = _PINNED.get(arr.ctypes.data)
+    return ent is not None and ent >= arr.nbytes
+
+
+def _unpin_address(addr: int):
+    if _PINNED.pop(addr, None) is not None and _lib is not None:
+        _lib.ta_host_unregister(c_void_p(addr))
+
+
+def pin_array(arr: np.ndarray) -> bool:
+    """Page-lock ``arr`` (cudaHostRegister) unless that has been done already; returns whether the array is pinned.
+    A failure (locked-memory limit, memory the driver cannot pin, a range the caller has already registered) is not
+    an error: copies from pageable memory work, through the driver's staging buffers."""
+    import weakref
+
+    if is_pinned(arr):
+        return True
+    lib = load_library()
+    addr = arr.ctypes.data
+    rc = lib.ta_host_register(c_void_p(addr), c_uint64(arr.nbytes))
+    if rc != 0:
+        # already registered by the caller (bench.py, a user who pins their own buffers) counts as pinned
+        return b"already" in (lib.ta_last_error(None) or b"")
+    _PINNED[addr] = arr.nbytes
+    owner = arr
+    while isinstance(getattr(owner, "base", None), np.ndarray):
+        owner = owner.base            # the object whose death frees the memory
+    try:
+        weakref.finalize(owner, _unpin_address, addr)
+    except TypeError:
+        pass                          # not weak-referenceable: stays pinned for the life of the process
+    return True

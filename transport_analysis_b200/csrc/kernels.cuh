@@ -430,6 +430,29 @@ k6_helfand_refine(const HelfandFftArgs a) {
 }
 
 // ---------------------------------------------------------------------------
+// Probe: the FP64 FMA rate of the whole device (bench.py's measured FP64 roofline denominator; MEASURED_PEAKS.json
+// holds HBM and bf16 figures only).  16 independent DFMA chains per thread, 8 warps per SM sub-partition.
+// ---------------------------------------------------------------------------
+constexpr int KP_CHAINS = 16, KP_UNROLL = 8, KP_THREADS = 256;
+__global__ void __launch_bounds__(KP_THREADS)
+k_probe_fp64(double* out, int iters, double a, double b) {
+    double x[KP_CHAINS];
+#pragma unroll
+    for (int i = 0; i < KP_CHAINS; ++i) x[i] = a + (double)(i + threadIdx.x);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < KP_UNROLL; ++rep) {
+#pragma unroll
+            for (int i = 0; i < KP_CHAINS; ++i) x[i] = fma(x[i], a, b);
+        }
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int i = 0; i < KP_CHAINS; ++i) sum += x[i];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = sum;
+}
+
+// ---------------------------------------------------------------------------
 // K4a: fixed-order sum of the per-CTA partial rows -> atom sum of this shard.
 // ---------------------------------------------------------------------------
 __global__ void k_sum_partials(const double* __restrict__ partial, int nrows, long long Tld, int T,

@@ -815,8 +815,11 @@ int ta_ctx_create_rank(int device, int rank, int nranks, const void* id128, ta_c
 void ta_ctx_destroy(ta_ctx* ctx) { destroy_ctx(ctx); }
 
 int ta_host_register(void* ptr, uint64_t bytes) {
-    ta_ctx* ctx = nullptr;
-    CK(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+    cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();               // not sticky: the caller may go on with pageable copies
+        return fail(nullptr, TA_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e));
+    }
     return TA_OK;
 }
 int ta_host_unregister(void* ptr) {
@@ -1120,6 +1123,7 @@ int ta_helfand_fft(ta_ctx* ctx, const double* volumes, double boltzmann, double 
         k5_helfand_fft_finish<<<grid, K5_THREADS, smem, s.s_compute>>>(a);
         CK(cudaGetLastError());
         ctx->launches++;
+        CK(cudaEventRecord(s.ev_kb, s.s_compute));                   // ta_last_kernel_ms: K1 + K5 (+ K6 below)
         CK(cudaMemcpyAsync(&nflag[i], counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.s_compute));
     }
     bool need_k3 = false;
@@ -1152,6 +1156,7 @@ int ta_helfand_fft(ta_ctx* ctx, const double* volumes, double boltzmann, double 
         k6_helfand_refine<<<grid, K5_THREADS, smem, s.s_compute>>>(a);
         CK(cudaGetLastError());
         ctx->launches++;
+        CK(cudaEventRecord(s.ev_kb, s.s_compute));                   // ta_last_kernel_ms: K1 + K5 + K6
     }
     return finish_timeseries(ctx, grids, ts_out);
 }
@@ -1215,6 +1220,61 @@ int ta_timer_end(ta_ctx* ctx, float* ms) {
         worst = std::max(worst, t);
     }
     *ms = worst;
+    return TA_OK;
+}
+
+int ta_probe_fp64(ta_ctx* ctx, double* tflops) {
+    if (!ctx || !tflops) return fail(ctx, TA_ERR_INVALID, "null argument");
+    Shard& s = ctx->sh[0];
+    CK(cudaSetDevice(s.dev));
+    const int grid = s.num_sms * 4, iters = 20000;           // 8 warps per sub-partition
+    double* out = nullptr;
+    CK(cudaMalloc(&out, (size_t)grid * KP_THREADS * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {                        // the first launch warms up
+        CK(cudaEventRecord(e0, s.s_compute));
+        k_probe_fp64<<<grid, KP_THREADS, 0, s.s_compute>>>(out, iters, 1.0000001, 1e-9);
+        CK(cudaEventRecord(e1, s.s_compute));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) best = std::min(best, ms);
+        ctx->launches++;
+    }
+    CK(cudaGetLastError());
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    CK(cudaFree(out));
+    const double flop = 2.0 * (double)grid * KP_THREADS * (double)iters * KP_UNROLL * KP_CHAINS;
+    *tflops = flop / ((double)best * 1e-3) / 1e12;
+    return TA_OK;
+}
+
+int ta_probe_h2d(ta_ctx* ctx, uint64_t bytes, double* gbps) {
+    if (!ctx || !gbps || bytes == 0) return fail(ctx, TA_ERR_INVALID, "null argument");
+    Shard& s = ctx->sh[0];
+    CK(cudaSetDevice(s.dev));
+    void *h = nullptr, *d = nullptr;
+    CK(cudaHostAlloc(&h, (size_t)bytes, cudaHostAllocPortable));
+    memset(h, 1, (size_t)bytes);
+    cudaError_t e = cudaMalloc(&d, (size_t)bytes);
+    if (e != cudaSuccess) { cudaFreeHost(h); return fail(ctx, TA_ERR_NOMEM, "ta_probe_h2d: cannot allocate the device buffer"); }
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaMemcpyAsync(d, h, (size_t)bytes, cudaMemcpyHostToDevice, s.s_copy));    // warm-up
+    CK(cudaStreamSynchronize(s.s_copy));
+    CK(cudaEventRecord(e0, s.s_copy));
+    for (int rep = 0; rep < 3; ++rep) CK(cudaMemcpyAsync(d, h, (size_t)bytes, cudaMemcpyHostToDevice, s.s_copy));
+    CK(cudaEventRecord(e1, s.s_copy));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d); cudaFreeHost(h);
+    *gbps = 3.0 * (double)bytes / ((double)ms * 1e-3) / 1e9;
     return TA_OK;
 }
 

@@ -19,7 +19,7 @@ import numpy as np
 
 from . import _lib
 from ._compat import AnalysisBase, NoDataError, UpdatingAtomGroup, constants
-from ._staging import FrameStager, LazyByParticle, resolve_devices
+from ._staging import FrameStager, LazyByParticle, gather_index, regular_frame_window, resolve_devices
 from .velocityautocorr import parse_dim_type
 
 
@@ -34,7 +34,7 @@ class ViscosityHelfand(AnalysisBase):
     linear_fit_window : (int, int), optional -- lag window of the linear fit
         whose slope is stored as ``results.viscosity``.
 
-    Extra keyword arguments: ``precision``, ``devices``, ``max_eager_bytes``
+    Extra keyword arguments: ``precision``, ``devices``, ``max_eager_bytes``, ``staging``, ``pin_host``
     as for :class:`~transport_analysis_b200.velocityautocorr.VelocityAutocorr`, and
 
     ``fft``  ``False`` (default): the direct O(T^2) lag sums of the reference for every lag (viscosity.py:210-226).
@@ -50,7 +50,8 @@ class ViscosityHelfand(AnalysisBase):
     """
 
     def __init__(self, atomgroup, temp_avg=300.0, dim_type="xyz", linear_fit_window=None,
-                 precision="fp64", devices=None, max_eager_bytes=1 << 26, fft=False, **kwargs):
+                 precision="fp64", devices=None, max_eager_bytes=1 << 26, fft=False, staging="auto", pin_host=True,
+                 **kwargs):
         super().__init__(atomgroup.universe.trajectory, **kwargs)
 
         if isinstance(atomgroup, UpdatingAtomGroup):
@@ -69,6 +70,9 @@ class ViscosityHelfand(AnalysisBase):
             raise ValueError("fft=True (FFT route of the Helfand MSD) needs precision='fp64'")
         self.fft = (precision == "fp64") if fft == "auto" else bool(fft)
         self._fft_auto = fft == "auto"
+        if staging not in ("auto", "per_frame"):
+            raise ValueError("staging must be 'auto' or 'per_frame'")
+        self._staging, self._pin_host = staging, bool(pin_host)
         self._devices = resolve_devices(devices)
         self._max_eager_bytes = int(max_eager_bytes)
 
@@ -92,12 +96,12 @@ class ViscosityHelfand(AnalysisBase):
         except KeyError:
             self.boltzmann = constants["Boltzman_constant"]
         self._stager = FrameStager(self._ctx or self._devices, self.n_frames, self.n_particles, self._dim, 2,
-                                   self._masses, self.precision)
+                                   self._masses, self.precision, self._pin_host)
+        self._gather_ix = gather_index(self.atomgroup.ix)
         reader = self._trajectory
         # the bulk path still needs a box volume for every frame
-        if getattr(reader, "dimensions_array", None) is not None:
-            self._stager.try_bulk(reader, self.atomgroup.ix, getattr(self, "start", None),
-                                  getattr(self, "stop", None), getattr(self, "step", None), True)
+        if self._staging == "auto" and getattr(reader, "dimensions_array", None) is not None:
+            self._stager.try_bulk(reader, self.atomgroup.ix, regular_frame_window(self), True)
 
     def _single_frame(self):
         ts = self._ts
@@ -110,7 +114,8 @@ class ViscosityHelfand(AnalysisBase):
         self._volumes[self._frame_index] = volume
         if self._stager.bulk_done:
             return
-        self._stager.add_frame(self._frame_index, self.atomgroup.velocities, self.atomgroup.positions)
+        # atomgroup.velocities / .positions are ts.velocities[ix] / ts.positions[ix]: gathered straight into the pinned slab
+        self._stager.add_frame(self._frame_index, ts.velocities, ts.positions, atom_ix=self._gather_ix)
 
     def _conclude(self):
         self._stager.finish()
