@@ -37,7 +37,9 @@ def test_reference_arm_line_has_every_contract_key(workload):
 
 def test_algorithmic_work_per_atom_frame_matches_the_survey():
     # 32 B (VACF) / 56 B (Helfand) per atom-frame; 491.5 flop at T = 10,000, 458.8 at T = 5,000
-    assert bench.BYTES_PER_AF == {"fft": 32.0, "windowed": 32.0, "helfand": 56.0, "helfand_direct": 56.0}
+    assert bench.BYTES_PER_AF == {"fft": 32.0, "windowed": 32.0, "helfand": 56.0, "helfand_direct": 56.0, "helfand_fft": 56.0}
+    # FP32 mode: float series in HBM (4 D bytes in), float64 per-particle rows (8 bytes out)
+    assert bench.BYTES_PER_AF_FP32["fft"] == 20.0 and bench.BYTES_PER_AF_FP32["helfand"] == 32.0
     assert bench.flops_per_af("fft", 10000) == pytest.approx(491.52, abs=0.01)
     assert bench.flops_per_af("fft", 5000) == pytest.approx(458.75, abs=0.01)
     assert bench.flops_per_af("windowed", 2000) == 3 * 2001
@@ -48,8 +50,17 @@ def test_algorithmic_work_per_atom_frame_matches_the_survey():
 
 def test_kernel_label_follows_the_plan_the_library_reports():
     assert "three-pass" in bench.k1_kernel_name({"radices": [20, 16, 16], "threads": 320})
-    assert "radix-8" in bench.k1_kernel_name({"radices": [12, 8, 8, 8], "threads": 768})
+    assert "float" in bench.k1_kernel_name({"radices": [20, 16, 16], "threads": 320}, "fp32")
     assert "general" in bench.k1_kernel_name({"radices": [8, 8, 4], "threads": 32})
+
+
+def test_tiled_synthetic_trajectory_gives_every_particle_its_own_series():
+    v = bench.synthetic_trajectory(50, 3 * bench.TILE_ATOMS + 5, seed=3, threads=2)
+    assert v.shape == (50, 3 * bench.TILE_ATOMS + 5, 3) and v.dtype == np.float32
+    a, b = v[:, 7], v[:, bench.TILE_ATOMS + 7]
+    assert np.allclose(b, a * np.float32(1.0 + 1 / 64.0)) and not np.array_equal(a, b)
+    assert np.array_equal(v[:, : bench.TILE_ATOMS], bench.synthetic_trajectory(50, bench.TILE_ATOMS, seed=3, threads=1))
+    assert abs(bench.sum_of_squares(v, threads=3) - float((v.astype(np.float64) ** 2).sum())) < 1e-6 * float((v.astype(np.float64) ** 2).sum())
 
 
 def test_numa_binding_degrades_to_a_note_without_nvml():

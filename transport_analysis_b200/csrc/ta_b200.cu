@@ -399,6 +399,18 @@ int check_ready(ta_ctx* ctx) {
     return TA_OK;
 }
 
+// Table uploads go through the COMPUTE stream and are complete on return.  A plain cudaMemcpy from pageable memory
+// returns once the data sits in the driver's staging buffer; its DMA is ordered on the legacy stream only, which the
+// library's non-blocking streams do not wait for -- with the copy engine busy streaming trajectory chunks an 80 KB
+// table reached the device AFTER the first K1 launches had read it (zeros for every chunk but the last: found in
+// round 2, profiles/r02_bulk_pipeline_race.txt).
+template <typename V>
+int upload_vec(ta_ctx* ctx, Shard& s, void** dst, const std::vector<V>& v) {
+    CK(cudaMalloc(dst, std::max<size_t>(v.size(), 1) * sizeof(V)));
+    if (!v.empty()) CK(cudaMemcpyAsync(*dst, v.data(), v.size() * sizeof(V), cudaMemcpyHostToDevice, s.s_compute));
+    return TA_OK;
+}
+
 template <typename R>
 int upload_fft_tables(ta_ctx* ctx, const std::vector<uint32_t>& own0) {
     const FftPlanHost& p = ctx->plan;
@@ -410,16 +422,12 @@ int upload_fft_tables(ta_ctx* ctx, const std::vector<uint32_t>& own0) {
         CK(cudaSetDevice(s.dev));
         cudaFree(s.tw_lo); cudaFree(s.tw_hi); cudaFree(s.ftab); cudaFree(s.pair0); cudaFree(s.own0);
         s.tw_lo = s.tw_hi = nullptr; s.ftab = s.pair0 = s.own0 = nullptr;
-        CK(cudaMalloc(&s.tw_lo, lo.size() * sizeof(cplx<R>)));
-        CK(cudaMalloc(&s.tw_hi, hi.size() * sizeof(cplx<R>)));
-        CK(cudaMalloc(&s.ftab, p.ftab.size() * sizeof(uint32_t)));
-        CK(cudaMalloc(&s.pair0, p.pair0.size() * sizeof(uint32_t)));
-        CK(cudaMalloc(&s.own0, own0.size() * sizeof(uint32_t)));
-        CK(cudaMemcpy(s.tw_lo, lo.data(), lo.size() * sizeof(cplx<R>), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(s.tw_hi, hi.data(), hi.size() * sizeof(cplx<R>), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(s.ftab, p.ftab.data(), p.ftab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(s.pair0, p.pair0.data(), p.pair0.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(s.own0, own0.data(), own0.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        int rc;
+        if ((rc = upload_vec(ctx, s, &s.tw_lo, lo)) || (rc = upload_vec(ctx, s, &s.tw_hi, hi)) ||
+            (rc = upload_vec(ctx, s, (void**)&s.ftab, p.ftab)) || (rc = upload_vec(ctx, s, (void**)&s.pair0, p.pair0)) ||
+            (rc = upload_vec(ctx, s, (void**)&s.own0, own0)))
+            return rc;
+        CK(cudaStreamSynchronize(s.s_compute));          // the host vectors go out of scope; the tables are in place
     }
     return TA_OK;
 }
@@ -432,15 +440,12 @@ int upload_fast_tables(ta_ctx* ctx, const K1FastPlan& p) {
         CK(cudaSetDevice(s.dev));
         cudaFree(s.f_omega); cudaFree(s.f_tw2); cudaFree(s.f_map); cudaFree(s.f_wbase); cudaFree(s.f_inv);
         s.f_omega = s.f_tw2 = s.f_wbase = s.f_inv = nullptr; s.f_map = nullptr;
-#define TA_UP(dst, vec)                                                                         \
-        CK(cudaMalloc((void**)&dst, vec.size() * sizeof(vec[0])));                              \
-        CK(cudaMemcpy(dst, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice));
-        TA_UP(s.f_omega, omega);
-        TA_UP(s.f_tw2, tw2);
-        TA_UP(s.f_map, p.map);
-        TA_UP(s.f_wbase, wbase);
-        TA_UP(s.f_inv, inv);
-#undef TA_UP
+        int rc;
+        if ((rc = upload_vec(ctx, s, &s.f_omega, omega)) || (rc = upload_vec(ctx, s, &s.f_tw2, tw2)) ||
+            (rc = upload_vec(ctx, s, (void**)&s.f_map, p.map)) || (rc = upload_vec(ctx, s, &s.f_wbase, wbase)) ||
+            (rc = upload_vec(ctx, s, &s.f_inv, inv)))
+            return rc;
+        CK(cudaStreamSynchronize(s.s_compute));
     }
     return TA_OK;
 }
@@ -854,7 +859,9 @@ int ta_stage_begin(ta_ctx* ctx, int64_t T, int64_t N, int D, const int* dims, in
         for (auto& s : ctx->sh) {
             if (s.natoms == 0 || n_fields != 2) continue;
             CK(cudaSetDevice(s.dev));
-            CK(cudaMemcpy(s.masses, masses + s.atom0, (size_t)s.natoms * sizeof(double), cudaMemcpyHostToDevice));
+            // on the stream K0 runs on, and complete on return (a plain cudaMemcpy is not ordered with it: see upload_vec)
+            CK(cudaMemcpyAsync(s.masses, masses + s.atom0, (size_t)s.natoms * sizeof(double), cudaMemcpyHostToDevice, s.s_compute));
+            CK(cudaStreamSynchronize(s.s_compute));
         }
         return TA_OK;
     }
@@ -912,7 +919,16 @@ int ta_stage_begin(ta_ctx* ctx, int64_t T, int64_t N, int D, const int* dims, in
         }
     }
     ctx->begun = true;
-    return sync_all(ctx);
+    int rc = sync_all(ctx);
+    if (rc) return rc;
+    // The FFT plan and its tables now, while the copy engine is idle: a compute call that follows ta_stage_bulk is
+    // queued behind the trajectory copies chunk by chunk, and a table upload issued then would wait for all of them.
+    // (Cheap: ~100 KB of tables.  A T the FFT route cannot plan is reported by the FFT compute calls, not here.)
+    if (ensure_fft_plan(ctx) != TA_OK) {
+        ctx->plan_T = -1;
+        ctx->err.clear();
+    }
+    return TA_OK;
 }
 
 int ta_stage_slot(ta_ctx* ctx, void** host_ptr, int64_t* frames_capacity) {
