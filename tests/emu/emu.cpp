@@ -75,7 +75,7 @@ static int run_win(const double* series_f64, int T, int D, int Tld, int mode, in
     std::vector<double> row(Tld, 0.0), partial(Tld, 0.0);
     WinArgs a;
     a.series = series; a.by_particle = row.data(); a.partial = partial.data();
-    a.natoms = 1; a.D = D; a.T = T; a.Tld = Tld; a.denom = 1.0;
+    a.natoms = 1; a.D = D; a.DS = D; a.T = T; a.Tld = Tld; a.denom = 1.0;
     a.scratch = nullptr; a.scratch_stride = 0;
     const int nthr = 32 * nwarps;
     if (mode == TA_WIN_PRODUCT) emu::run_cta(nthr, [&](int tid) { win_body<R, TA_WIN_PRODUCT, emu::EmuCtx>(a, sm, tid, nthr, 0, 1); });
@@ -103,7 +103,7 @@ static int run_k1fast(const double* series_f64, int T, int D, int Tld, int natom
     a.map = p.map.data();
     a.wbase = reinterpret_cast<const cplx<RT>*>(wbase.data());
     a.inv = inv.data();
-    a.natoms = natoms; a.D = D; a.T = T; a.nh = p.nh; a.Tld = Tld;
+    a.natoms = natoms; a.D = D; a.DS = D; a.T = T; a.nh = p.nh; a.Tld = Tld;
     constexpr bool PREF = k1f_prefetch(R1, (int)sizeof(RT));        // the build the library ships for this (R1, RT)
     std::vector<unsigned char> smem(k1f_smem_bytes(R1, PREF, (int)sizeof(RT)) + 64);
     unsigned char* sm = smem.data() + (16 - ((uintptr_t)smem.data() & 15)) % 16;

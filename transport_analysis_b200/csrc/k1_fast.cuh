@@ -50,7 +50,7 @@ namespace ta {
 
 template <typename RT>
 struct K1FArgs {
-    const RT* series;            // [natoms][D][Tld]
+    const RT* series;            // [natoms][DS][Tld]: the first D rows of a particle are transformed (DS > D: Helfand keeps a row of sum_d g^2 behind them)
     double* by_particle;         // [natoms][Tld]
     double* partial;             // [grid][Tld]
     const cplx<RT>* omega;       // [256]      w_{2H}^j
@@ -58,7 +58,7 @@ struct K1FArgs {
     const uint32_t* map;         // [2][16 R1] per residue: bits 0-15 P3 butterfly of a thread, 16-23 its P2 block, 30/31 flags
     const cplx<RT>* wbase;       // [2][16 R1] w_L^{2 G0 + r} of that butterfly
     const RT* inv;               // [Tld]      1 / (L (T - k)), 0 beyond T
-    int natoms, D, T, nh;
+    int natoms, D, DS, T, nh;
     long long Tld;
 };
 
@@ -135,13 +135,13 @@ TA_HD void k1f_body(const K1FArgs<RT>& A, unsigned char* smem_raw, int tid, int 
     // bytes of one series the bulk copy moves: nh complex values, rounded up to the 16 bytes the engine works in
     // (FP32: the extra 8 bytes are the zero padding of the row, Tld is a multiple of 16 elements)
     const unsigned ser_bytes = ((unsigned)nh * (unsigned)sizeof(C) + 15u) & ~15u;
-    if (PREF && tid == 0 && bid < A.natoms) Ctx::bulk_load(pre, A.series + (size_t)bid * A.D * A.Tld, ser_bytes, mbar);
+    if (PREF && tid == 0 && bid < A.natoms) Ctx::bulk_load(pre, A.series + (size_t)bid * A.DS * A.Tld, ser_bytes, mbar);
     const int j2 = tid & 15;                         // NT is a multiple of 16: the same for every owned butterfly
     cd* part = reinterpret_cast<cd*>(A.partial + (size_t)bid * A.Tld);
     const C* inv2 = reinterpret_cast<const C*>(A.inv);
 
     for (int atom = bid; atom < A.natoms; atom += nblk) {
-        const RT* ser = A.series + (size_t)atom * A.D * A.Tld;
+        const RT* ser = A.series + (size_t)atom * A.DS * A.Tld;
         cd* row = reinterpret_cast<cd*>(A.by_particle + (size_t)atom * A.Tld);
         for (int r = 0; r < 2; ++r) {
             RT acc_s[NB][8], acc_d[NB][8], acc8[NB];
@@ -199,7 +199,7 @@ TA_HD void k1f_body(const K1FArgs<RT>& A, unsigned char* smem_raw, int tid, int 
                         const RT* nxt = nullptr;
                         if (d + 1 < A.D) nxt = ser + (size_t)(d + 1) * A.Tld;
                         else if (r == 0) nxt = ser;
-                        else if (atom + nblk < A.natoms) nxt = ser + (size_t)nblk * A.D * A.Tld;
+                        else if (atom + nblk < A.natoms) nxt = ser + (size_t)nblk * A.DS * A.Tld;
                         if (nxt) Ctx::bulk_load(pre, nxt, ser_bytes, mbar);
                     }
                 }

@@ -28,8 +28,11 @@ template <typename SRC, bool HELFAND, typename OUT>
 __global__ void __launch_bounds__(256)
 k0_stage(const SRC* __restrict__ v, const SRC* __restrict__ x, const double* __restrict__ masses,
          OUT* __restrict__ series, int natoms, int nframes, long long frame0, long long Tld,
-         int D, int d0, int d1, int d2) {
-    // frames on grid.x (2^31 - 1 tiles: any T the library accepts), particles on grid.y, tiled further by the loop below
+         int D, int DS, int d0, int d1, int d2) {
+    // frames on grid.x (2^31 - 1 tiles: any T the library accepts), particles on grid.y, tiled further by the loop below.
+    // A particle owns DS rows of Tld values: its D selected columns and, when DS > D (Helfand in FP64), a row of
+    // q[i] = sum_d g_d[i]^2 -- what the O(T log T) route's finishing kernel K5 prefix-sums (it then reads 8 bytes per
+    // atom-frame instead of the 8 D of the series).
     __shared__ OUT tile[K0_FR][K0_AT * 3 + 1];
     const int f0 = blockIdx.x * K0_FR;
     const int nf = min(K0_FR, nframes - f0);
@@ -49,12 +52,20 @@ k0_stage(const SRC* __restrict__ v, const SRC* __restrict__ x, const double* __r
             }
         }
         __syncthreads();
-        const int nrows = na * D;
+        const int nrows = na * DS;
         for (int r = threadIdx.y; r < nrows; r += blockDim.y) {
-            const int a = r / D, d = r - a * D;
-            OUT* dst = series + ((size_t)(a0 + a) * D + d) * Tld + frame0 + f0;
-            const int col = a * 3 + dims[d];
-            for (int f = threadIdx.x; f < nf; f += blockDim.x) dst[f] = tile[f][col];
+            const int a = r / DS, d = r - a * DS;
+            OUT* dst = series + ((size_t)(a0 + a) * DS + d) * Tld + frame0 + f0;
+            if (d < D) {
+                const int col = a * 3 + dims[d];
+                for (int f = threadIdx.x; f < nf; f += blockDim.x) dst[f] = tile[f][col];
+            } else {
+                for (int f = threadIdx.x; f < nf; f += blockDim.x) {
+                    double q = 0.0;
+                    for (int e = 0; e < D; ++e) { const double g = (double)tile[f][a * 3 + dims[e]]; q = fma(g, g, q); }
+                    dst[f] = (OUT)q;
+                }
+            }
         }
         __syncthreads();
     }
@@ -67,10 +78,10 @@ template <typename R>
 struct K1Args {
     FftTables<R> t;              // tw_lo / tw_hi point to GLOBAL copies here
     int nlo, nhi;
-    const R* series;             // [natoms][D][Tld]  (stored in the arithmetic type)
+    const R* series;             // [natoms][DS][Tld]  (stored in the arithmetic type; the first D rows are transformed)
     double* by_particle;         // [natoms][Tld]
     double* partial;             // [gridDim.x][Tld]
-    int natoms, D;
+    int natoms, D, DS;
     long long Tld;
     unsigned char* scratch;      // SCRATCH: per-CTA work area in global memory (FFT buffer + pair accumulators)
     long long scratch_stride;    // bytes per CTA
@@ -102,7 +113,7 @@ k1_fft_acf(const K1Args<R> args) {
 
     double* partial = args.partial + (size_t)blockIdx.x * args.Tld;
     for (int a = blockIdx.x; a < args.natoms; a += gridDim.x) {
-        const R* ser = args.series + (size_t)a * args.D * args.Tld;
+        const R* ser = args.series + (size_t)a * args.DS * args.Tld;
         double* row = args.by_particle + (size_t)a * args.Tld;
         for (int r = 0; r < 2; ++r) {
             fft_zero_acc<R>(tid, nthr, sd, t);
@@ -204,10 +215,11 @@ struct DevCtx {
     static TA_HD void mbar_wait(unsigned long long* bar, unsigned parity) {
 #if defined(__CUDA_ARCH__)
         const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-        unsigned done = 0;
+        unsigned done = 0, tries = 0;
         while (!done) {
             asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
                          : "=r"(done) : "r"(a), "r"(parity) : "memory");
+            if (!done && ++tries > (1u << 22)) __trap();          // a bulk copy that never lands is a bug: fail, do not hang
         }
 #endif
     }
@@ -256,176 +268,231 @@ k_windowed(const WinArgs args) {
 // same quantity as ViscosityHelfand._conclude, viscosity.py:201-233):
 //   sum_i (g[i] - g[i+k])^2 = S1[k] - 2 S2[k],
 //   S2[k] = sum_i g[i] g[i+k]                      (K1 left  sum_d S2_d[k] / (T-k)  in by_particle)
-//   S1[k] = sum_{i<T-k} g[i]^2 + sum_{i>=k} g[i]^2 (from one prefix sum of q[i] = sum_d g_d[i]^2)
-// One CTA per particle at a time; prefix sums in shared memory.  The difference cancels, so the
-// relative error grows like eps * S1 / MSD (largest at small lags): this route is opt-in.
+//   S1[k] = sum_{i<T-k} q[i] + sum_{i>=k} q[i],    q[i] = sum_d g_d[i]^2   (the extra series row K0 wrote)
+// The difference cancels: both terms carry rounding errors of C eps sum g^2 (C = 9 - 33 measured,
+// profiles/r02_helfand_fft_error_constant.txt), so a lag whose un-normalised MSD is below thr * sum g^2 is NOT good to
+// 1e-10 and goes on a list that K6 evaluates with the reference's own sum.
+//
+// One CTA of 32 warps per SM, persistent over particles b, b + grid, ...  Per particle: the q row arrives by the
+// bulk-copy engine (TMA) into one of two shared buffers -- the row of the NEXT particle is in flight while this one is
+// worked on --, each warp scans its contiguous 1/32 of the row with shuffle scans (no bank conflicts), one barrier,
+// then thread t finishes lags t, t + 1024, ...: two prefix-sum reads, the row K1 left, the value, the test.  The
+// lag k is always handled by thread k % 1024 (warp (k / 32) % 32), which alone updates entry k of the CTA's
+// particle-sum row, and each warp appends the lags it marks to ITS OWN list (a counter in a register: no atomics, and the
+// order -- hence every later floating-point sum -- is the same in every run).  HBM traffic: 8 (q) + 8 (row in) +
+// 8 (row out) bytes per atom-frame.
 // ---------------------------------------------------------------------------
 struct HelfandFftArgs {
-    const double* series;   // [natoms][D][Tld]
+    const double* series;   // [natoms][DS][Tld]; row D of a particle is q
     double* by_particle;    // [natoms][Tld]  in: sum_d acf_d ; out: viscosity function
-    double* partial;        // [gridDim.x][Tld]   (K6)
-    int natoms, D, T;
+    double* partial;        // [gridDim.x][Tld]   particle sums of this CTA's rows (K5 writes, K6 corrects)
+    int natoms, D, DS, T;
     long long Tld;
     double denom;           // 2 kB <V> temp_avg
-    uint32_t* flags;        // [natoms][nwords]  bit k of a particle: lag k needs the exact evaluation
-    int nwords;             // ceil(T / 32)
-    unsigned long long* nflagged;   // total number of flagged (particle, lag) pairs
-    double thr;             // a lag is flagged when its un-normalised MSD is below thr * sum_i sum_d g^2
+    unsigned long long* list;   // [gridDim.x * 32][cap]  (particle << 32 | lag) pairs that need the exact evaluation, per warp
+    unsigned* count;            // [gridDim.x * 32]       entries of each list (may exceed cap: the excess was dropped -> overflow)
+    unsigned long long* total;  // [2]  sum of all counts; number of lists that overflowed
+    unsigned cap;
+    double thr;             // a lag is marked when its un-normalised MSD is below thr * sum_i sum_d g^2
+    int nbuf;               // K5: shared q / prefix-sum buffers (2: next row prefetched; 1: series too long for two)
 };
 
-constexpr int K5_THREADS = 1024;
+constexpr int K5_THREADS = 512;
+constexpr int K5_WARPS = K5_THREADS / 32;
 
-// K5: S1[k] - 2 S2[k] per particle.  Both terms are of the size of sum g^2 and carry rounding errors of that size
-// (C eps sum g^2: the FFT autocorrelation and the prefix sums), so the difference is only as accurate as
-// C eps sum g^2 / MSD[k] relative.  Lags whose MSD is too small for the 1e-10 bar (short lags of smooth series, the last
-// lags of any series) are marked in a per-particle bitmap and evaluated exactly by K6.
-__global__ void __launch_bounds__(K5_THREADS)
+// 1 / a for a > 0: hardware seed + two Newton steps (within 1 ulp; no division sequence)
+__device__ __forceinline__ double rcp_pos(double a) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double e = fma(-a, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-a, y, 1.0);
+    return fma(y, e, y);
+}
+
+// MINB = 2: compiled for two co-resident CTAs (64 registers) with one q buffer each, which cover each other's load
+// latencies -- 7.3 ms at 125,000 x 10,000 against 11.0 ms for one CTA with two buffers, whether or not that one has
+// every row value in registers before its scan starts (profiles/r02_k5_k6.txt); MINB = 1: rows too long for two CTAs.
+template <int MINB>
+__global__ void __launch_bounds__(K5_THREADS, MINB)
 k5_helfand_fft_finish(const HelfandFftArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* P = reinterpret_cast<double*>(smem_raw);   // P[j] = sum_{i<j} q[i], j = 0..T
-    __shared__ double wsum[K5_THREADS / 32];
-    __shared__ unsigned cta_flagged;
     const int T = a.T, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int seg = (T + K5_THREADS - 1) / K5_THREADS;
-    const int lo = min(T, tid * seg), hi = min(T, lo + seg);
-    if (tid == 0) cta_flagged = 0;
-    double* partial = a.partial + (size_t)blockIdx.x * a.Tld;   // particle sum of the rows as K5 leaves them; K6 corrects it
-    for (int n = blockIdx.x; n < a.natoms; n += gridDim.x) {
-        const double* ser = a.series + (size_t)n * a.D * a.Tld;
-        __syncthreads();   // previous particle's P fully consumed
-        // q[i] into P[i + 1] (coalesced), then a three-level inclusive scan
-        for (int i0 = 0; i0 < T; i0 += 4 * K5_THREADS) {       // four samples per thread in flight
-            double q[4] = {0.0, 0.0, 0.0, 0.0};
-            for (int d = 0; d < a.D; ++d) {
-                double gv[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { const int i = i0 + j * K5_THREADS + tid; gv[j] = i < T ? ser[(size_t)d * a.Tld + i] : 0.0; }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) q[j] = fma(gv[j], gv[j], q[j]);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { const int i = i0 + j * K5_THREADS + tid; if (i < T) P[i + 1] = q[j]; }
-        }
-        if (tid == 0) P[0] = 0.0;
-        __syncthreads();
+    const unsigned row_bytes = (unsigned)a.Tld * (unsigned)sizeof(double);          // Tld is a multiple of 16 values
+    double* bufs[2] = {reinterpret_cast<double*>(smem_raw), reinterpret_cast<double*>(smem_raw + (a.nbuf > 1 ? row_bytes : 0))};
+    __shared__ double wsum[K5_WARPS];
+    __shared__ __align__(8) unsigned long long mbar[2];
+    const int nj = (T + K5_THREADS - 1) / K5_THREADS;               // lags per thread
+    const int R = nj | 1;                                           // values per lane in the scan: odd -> conflict-free 64-bit accesses
+    const int C = 32 * R;                                           // values per warp
+    const unsigned magicC = (unsigned)((0x100000000ull + (unsigned)C - 1) / (unsigned)C);   // i / C = umulhi(i, magicC) for i < 2^32 / C
+    double* partial = a.partial + (size_t)blockIdx.x * a.Tld;       // zeroed by the host; stays L2-resident (one row per CTA)
+    unsigned my_count = 0;                                          // warp-uniform: entries this warp has appended
+    unsigned long long* my_list = a.list + ((size_t)blockIdx.x * K5_WARPS + warp) * a.cap;
+    const double cscale = 1.0 / ((double)a.D * a.denom);
+
+    if (tid == 0) { DevCtx::mbar_init(&mbar[0]); DevCtx::mbar_init(&mbar[1]); }
+    __syncthreads();
+    auto qrow = [&](int n) { return a.series + ((size_t)n * a.DS + a.D) * a.Tld; };
+    if (tid == 0 && (int)blockIdx.x < a.natoms) DevCtx::bulk_load(bufs[0], qrow(blockIdx.x), row_bytes, &mbar[0]);
+    unsigned phase0 = 0u, phase1 = 0u;
+    int it = 0;
+    for (int n = blockIdx.x; n < a.natoms; n += gridDim.x, ++it) {
+        const int b = a.nbuf > 1 ? (it & 1) : 0;
+        double* P = bufs[b];                                       // q, then its inclusive prefix sums within each warp's stretch
+        double* row = a.by_particle + (size_t)n * a.Tld;
+        if (a.nbuf > 1 && tid == 0 && n + (int)gridDim.x < a.natoms)
+            DevCtx::bulk_load(bufs[b ^ 1], qrow(n + gridDim.x), row_bytes, &mbar[b ^ 1]);      // its readers left it at the last barrier
+        if (b == 0) { DevCtx::mbar_wait(&mbar[0], phase0); phase0 ^= 1u; }
+        else { DevCtx::mbar_wait(&mbar[1], phase1); phase1 ^= 1u; }
+        // ---- scan: warp w owns values [w C, (w + 1) C), lane l the run [w C + l R, + R)
+        const int i0 = warp * C + lane * R;
         double run = 0.0;
-        for (int i = lo; i < hi; ++i) { run += P[i + 1]; P[i + 1] = run; }
-        double incl = run;   // inclusive scan of the segment totals over the block
+        for (int t = 0; t < R; ++t) {
+            const int i = i0 + t;
+            if (i < T) { run += P[i]; P[i] = run; }
+        }
+        double incl = run;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const double v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
+            const double u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        const double lo = incl - run;                               // sum of the runs of the lanes below
+        for (int t = 0; t < R; ++t) {
+            const int i = i0 + t;
+            if (i < T) P[i] += lo;
         }
         if (lane == 31) wsum[warp] = incl;
         __syncthreads();
-        double base = incl - run;
-        for (int w = 0; w < warp; ++w) base += wsum[w];
-        for (int i = lo; i < hi; ++i) P[i + 1] += base;
-        __syncthreads();
-        double* row = a.by_particle + (size_t)n * a.Tld;
-        uint32_t* fl = a.flags + (size_t)n * a.nwords;
-        const double tot = P[T];
-        const double floor_msd = a.thr * tot;
-        const double cscale = 1.0 / ((double)a.D * a.denom);
-        unsigned mine = 0;
-        // lags k = k0 + tid, in batches of KB: the global loads of a batch (row, partial) are issued together;
-        // uniform trip count (the ballot needs whole warps)
-        constexpr int KB = 4;
-        for (int k0 = 0; k0 < T; k0 += KB * K5_THREADS) {
-            double r[KB], pa[KB];
+        // every warp: exclusive scan of the stretch totals (lane l < 16 holds the offset of stretch l)
+        double woff = lane < K5_WARPS ? wsum[lane] : 0.0, tot;
+        {
+            double inc2 = woff;
 #pragma unroll
-            for (int j = 0; j < KB; ++j) {
-                const int k = k0 + j * K5_THREADS + tid;
-                r[j] = k < T ? row[k] : 0.0;
-                pa[j] = k < T ? partial[k] : 0.0;
+            for (int o = 1; o < K5_WARPS; o <<= 1) {
+                const double u = __shfl_up_sync(0xffffffffu, inc2, o);
+                if (lane >= o) inc2 += u;
             }
-#pragma unroll
-            for (int j = 0; j < KB; ++j) {
-                const int k = k0 + j * K5_THREADS + tid;
-                bool flag = false;
-                if (k < T) {
-                    double val = 0.0;                           // lag 0 stays exactly 0 (viscosity.py:207-210)
-                    if (k > 0) {
-                        const double s1 = P[T - k] + (tot - P[k]);
-                        const double nk = (double)(T - k);
-                        const double msd = s1 - 2.0 * r[j] * nk;    // un-normalised, what the threshold is about
-                        flag = !(msd >= floor_msd);                 // also catches a NaN
-                        val = (s1 / nk - 2.0 * r[j]) * cscale;
-                    }
-                    row[k] = val;
-                    partial[k] = pa[j] + val;
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, flag);
-                if (lane == 0 && k < T) { fl[k >> 5] = m; mine += __popc(m); }
-            }
+            tot = __shfl_sync(0xffffffffu, inc2, K5_WARPS - 1);
+            woff = inc2 - woff;
         }
-        if (lane == 0 && mine) atomicAdd(&cta_flagged, mine);
+        // prefix sum Pj = sum_{i<j} q[i], j = 0 .. T (all lanes call it: the stretch offset travels by shuffle)
+        auto prefix = [&](int j) {
+            const int i = j > 0 ? j - 1 : 0;
+            const double off = __shfl_sync(0xffffffffu, woff, (int)__umulhi((unsigned)i, magicC));
+            return j > 0 ? P[i] + off : 0.0;
+        };
+        const double floor_msd = a.thr * tot;
+        // one lag: value, test, list entry (all lanes of the warp call it together)
+        auto finish_lag = [&](int k, double rk, double pak) {
+            const int kc = k < T ? k : 0;
+            const double pk = prefix(kc), ptk = prefix(T - kc);
+            bool flag = false;
+            if (k < T) {
+                double val = 0.0;                                   // lag 0 stays exactly 0 (viscosity.py:207-210)
+                if (k > 0) {
+                    const double s1 = ptk + (tot - pk);
+                    const double nk = (double)(T - k);
+                    const double msd = s1 - 2.0 * rk * nk;          // un-normalised, what the threshold is about
+                    flag = !(msd >= floor_msd);                     // also catches a NaN
+                    val = msd * rcp_pos(nk) * cscale;
+                }
+                __stcs(row + k, val);
+                partial[k] = pak + (flag ? 0.0 : val);              // a marked lag enters the sum with its exact value, in K6
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, flag);
+            if (flag) {
+                const unsigned idx = my_count + __popc(m & ((1u << lane) - 1u));
+                if (idx < a.cap) my_list[idx] = ((unsigned long long)(unsigned)n << 32) | (unsigned)k;
+            }
+            my_count += __popc(m);
+        };
+        for (int j0 = 0; j0 < nj; j0 += 4) {                        // the row K1 left and this CTA's sum row, four lags at a time
+            double r4[4], p4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = tid + (j0 + u) * K5_THREADS;
+                const bool in = j0 + u < nj && k < T;
+                r4[u] = in ? __ldcs(row + k) : 0.0;
+                p4[u] = in ? partial[k] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (j0 + u < nj) finish_lag(tid + (j0 + u) * K5_THREADS, r4[u], p4[u]);       // uniform over the CTA
+        }
+        __syncthreads();                                            // P is free: the next-but-one row may land in it
+        if (a.nbuf == 1 && tid == 0 && n + (int)gridDim.x < a.natoms)
+            DevCtx::bulk_load(bufs[0], qrow(n + gridDim.x), row_bytes, &mbar[0]);
     }
-    __syncthreads();
-    if (tid == 0 && cta_flagged) atomicAdd(a.nflagged, (unsigned long long)cta_flagged);
+    if (lane == 0) {
+        a.count[(size_t)blockIdx.x * K5_WARPS + warp] = my_count;
+        if (my_count) atomicAdd(a.total, (unsigned long long)my_count);
+        if (my_count > a.cap) atomicAdd(a.total + 1, 1ull);
+    }
 }
 
-// K6: exact evaluation of the flagged lags, sum_d sum_i (g_d[i] - g_d[i+k])^2 (viscosity.py:212-226; one warp per lag, lanes
-// stride the origins, fixed-order reduction); the row takes the exact value and the per-CTA partial row (the particle sum K5
-// formed, same CTA -> particle map) the difference.  A particle whose flagged lags add up to little work (the usual case: the
-// last one or two lags, a handful of origins) reads its few samples straight from global memory; otherwise its series are
-// staged in shared memory one dimension at a time.
+// K6: the marked lags, evaluated with the reference's own sum  sum_d sum_i (g_d[i] - g_d[i+k])^2  (viscosity.py:212-226).
+// Same grid as K5.  Phase A: the entries of all the CTA's lists are dealt to all its warps (the last lags of every particle
+// sit on one or two lists) -- entries with few origins 32 at a time, one lane each, long ones one at a time with the lanes
+// striding the origins -- and the exact value replaces the row entry.  Phase B: warp w walks the list warp w of K5 wrote,
+// in order, and adds the exact values to the entries of the CTA's particle-sum row that only it touches (K5 left the
+// marked lags out of that sum): fixed order, no atomics, the same bits in every run.
+constexpr int K6_SHORT = 64;    // origins up to which an entry is a lane's job
+
 __global__ void __launch_bounds__(K5_THREADS)
 k6_helfand_refine(const HelfandFftArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* g = reinterpret_cast<double*>(smem_raw);   // one series of the particle (staged particles only)
-    __shared__ unsigned long long work_sum;
-    const int T = a.T, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = K5_THREADS / 32;
-    double* partial = a.partial + (size_t)blockIdx.x * a.Tld;
-    for (int n = blockIdx.x; n < a.natoms; n += gridDim.x) {
-        const double* ser = a.series + (size_t)n * a.D * a.Tld;
-        double* row = a.by_particle + (size_t)n * a.Tld;
-        const uint32_t* fl = a.flags + (size_t)n * a.nwords;
-        __syncthreads();
-        if (tid == 0) work_sum = 0ull;
-        __syncthreads();
-        unsigned long long w_mine = 0ull;               // origins to visit: sum over flagged lags of (T - k)
-        for (int w = tid; w < a.nwords; w += K5_THREADS) {
-            uint32_t m = fl[w];
-            while (m) { const int k = (w << 5) + __ffs(m) - 1; m &= m - 1; w_mine += (unsigned long long)(T - k); }
-        }
-        if (w_mine) atomicAdd(&work_sum, w_mine);
-        __syncthreads();
-        const unsigned long long work = work_sum;
-        if (work == 0ull) continue;
-        const bool staged = work > 4ull * (unsigned long long)T;
+    const int T = a.T, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double cscale = 1.0 / ((double)a.D * a.denom);
+    auto exact = [&](int n, int k, int i0, int istep) {            // sum over the origins i0, i0 + istep, ... of all dimensions
+        const double* ser = a.series + (size_t)n * a.DS * a.Tld;
+        double acc = 0.0;
         for (int d = 0; d < a.D; ++d) {
             const double* sd = ser + (size_t)d * a.Tld;
-            if (staged) {
-                __syncthreads();
-                for (int i = tid; i < T; i += K5_THREADS) g[i] = sd[i];
-                __syncthreads();
-            }
-            const double* src = staged ? g : sd;
-            for (int w = warp; w < a.nwords; w += NW) {  // flagged lags of this particle, dealt to the warps word by word
-                uint32_t m = fl[w];
-                while (m) {
-                    const int k = (w << 5) + __ffs(m) - 1;
-                    m &= m - 1;
-                    double acc = 0.0;
-                    for (int i = lane; i < T - k; i += 32) { const double df = src[i] - src[i + k]; acc = fma(df, df, acc); }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                    if (lane == 0) {
-                        // the running exact sum over the dimensions waits in the row itself; what K5 had put there leaves
-                        // the particle sum first and the exact value enters it after the last dimension
-                        if (d == 0) { partial[k] -= row[k]; row[k] = acc; }
-                        else row[k] += acc;
-                        if (d == a.D - 1) {
-                            const double e = row[k] / (double)(T - k) / (double)a.D / a.denom;
-                            row[k] = e;
-                            partial[k] += e;
-                        }
-                    }
-                }
-            }
+            for (int i = i0; i < T - k; i += istep) { const double df = sd[i] - sd[i + k]; acc = fma(df, df, acc); }
         }
+        return acc;
+    };
+    // ---- phase A
+    for (int lw = 0; lw < K5_WARPS; ++lw) {
+        const unsigned cnt = min(a.count[(size_t)blockIdx.x * K5_WARPS + lw], a.cap);
+        const unsigned long long* list = a.list + ((size_t)blockIdx.x * K5_WARPS + lw) * a.cap;
+        for (unsigned e = threadIdx.x; e < cnt; e += K5_THREADS) {                       // short entries: a lane each
+            const unsigned long long ent = list[e];
+            const int n = (int)(ent >> 32), k = (int)(ent & 0xffffffffu);
+            if (T - k > K6_SHORT) continue;
+            a.by_particle[(size_t)n * a.Tld + k] = exact(n, k, 0, 1) / (double)(T - k) * cscale;
+        }
+        for (unsigned e = warp; e < cnt; e += K5_WARPS) {                                 // long entries: a warp each
+            const unsigned long long ent = list[e];
+            const int n = (int)(ent >> 32), k = (int)(ent & 0xffffffffu);
+            if (T - k <= K6_SHORT) continue;                                              // uniform over the warp
+            double acc = exact(n, k, lane, 32);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) a.by_particle[(size_t)n * a.Tld + k] = acc / (double)(T - k) * cscale;
+        }
+    }
+    __syncthreads();            // the exact values written by the other warps of this CTA are visible
+    // ---- phase B
+    const unsigned n_ent = min(a.count[(size_t)blockIdx.x * K5_WARPS + warp], a.cap);
+    const unsigned long long* my_list = a.list + ((size_t)blockIdx.x * K5_WARPS + warp) * a.cap;
+    double* partial = a.partial + (size_t)blockIdx.x * a.Tld;
+    for (unsigned e0 = 0; e0 < n_ent; e0 += 32) {
+        const unsigned e = e0 + lane;
+        const bool mine = e < n_ent;
+        const unsigned long long ent = mine ? my_list[e] : 0ull;
+        const int n = (int)(ent >> 32), k = (int)(ent & 0xffffffffu);
+        const double v = mine ? a.by_particle[(size_t)n * a.Tld + k] : 0.0;
+        // the values of one lag, summed in lane (= particle) order by the first lane that holds it, then one update of the sum row
+        const unsigned same = __match_any_sync(0xffffffffu, mine ? k : -1 - lane);
+        double sum = 0.0;
+        for (int src = 0; src < 32; ++src) {                        // uniform trip count: every lane takes part in every shuffle
+            const double dv = __shfl_sync(0xffffffffu, v, src);
+            if ((same >> src) & 1u) sum += dv;
+        }
+        if (mine && lane == __ffs(same) - 1) partial[k] += sum;
+        __syncwarp();
     }
 }
 

@@ -121,7 +121,7 @@ struct Shard {
     uint32_t* f_map = nullptr;
     void* f_wbase = nullptr;
     void* f_inv = nullptr;
-    // FFT route of the Helfand MSD: per-particle bitmaps of the lags that need the exact evaluation (+ a counter)
+    // FFT route of the Helfand MSD: counters + per-warp lists of the (particle, lag) pairs that need the exact evaluation
     uint32_t* hflags = nullptr;
     size_t hflags_bytes = 0;
 };
@@ -137,6 +137,7 @@ struct ta_ctx {
     bool begun = false;
     int64_t T = 0, N = 0, Tld = 0;
     int D = 0, dims[3] = {0, 1, 2};
+    int DS = 0;              // series rows per particle: D, + 1 row of sum_d g^2 for Helfand in FP64 (K5 reads it)
     int src_dtype = TA_DTYPE_F32, n_fields = 1, precision = TA_PRECISION_FP64;
     size_t elt = 4;
     int64_t frames_staged = 0;
@@ -278,12 +279,12 @@ int launch_k0_t(ta_ctx* ctx, Shard& s, const void* vsrc, const void* xsrc, int64
     // frames on grid.x (up to 2^31 - 1 tiles), particle tiles on grid.y (the kernel loops when there are more than 65,535)
     dim3 grid((unsigned)((nframes + K0_FR - 1) / K0_FR), (unsigned)std::min<int64_t>((n + K0_AT - 1) / K0_AT, 65535));
     const int d0 = ctx->dims[0], d1 = ctx->dims[1], d2 = ctx->dims[2];
-    OUT* series = (OUT*)s.series + (size_t)a0 * ctx->D * ctx->Tld;
+    OUT* series = (OUT*)s.series + (size_t)a0 * ctx->DS * ctx->Tld;
     const double* masses = s.masses ? s.masses + a0 : nullptr;
     const SRC* v = (const SRC*)vsrc;
     const SRC* x = (const SRC*)xsrc;
-    if (ctx->n_fields == 2) k0_stage<SRC, true, OUT><<<grid, block, 0, stream>>>(v, x, masses, series, (int)n, (int)nframes, frame0, ctx->Tld, ctx->D, d0, d1, d2);
-    else k0_stage<SRC, false, OUT><<<grid, block, 0, stream>>>(v, x, masses, series, (int)n, (int)nframes, frame0, ctx->Tld, ctx->D, d0, d1, d2);
+    if (ctx->n_fields == 2) k0_stage<SRC, true, OUT><<<grid, block, 0, stream>>>(v, x, masses, series, (int)n, (int)nframes, frame0, ctx->Tld, ctx->D, ctx->DS, d0, d1, d2);
+    else k0_stage<SRC, false, OUT><<<grid, block, 0, stream>>>(v, x, masses, series, (int)n, (int)nframes, frame0, ctx->Tld, ctx->D, ctx->DS, d0, d1, d2);
     CK(cudaGetLastError());
     ctx->launches++;
     return TA_OK;
@@ -531,13 +532,13 @@ int launch_fft(ta_ctx* ctx, std::vector<int>* grids) {
         a.t.ftab = s.ftab; a.t.pair0 = s.pair0; a.t.own0 = s.own0; a.t.npairs0 = ctx->npairs0;
         a.nlo = nlo; a.nhi = nhi;
         a.partial = s.partial;
-        a.D = ctx->D; a.Tld = ctx->Tld;
+        a.D = ctx->D; a.DS = ctx->DS; a.Tld = ctx->Tld;
         a.scratch = in_smem ? nullptr : (unsigned char*)s.win_scratch;
         a.scratch_stride = (long long)work;
         CK(cudaEventRecord(s.ev_ka, s.s_compute));
         for (const LaunchRange& rg : take_launch_ranges(s)) {
             if (rg.ready) CK(cudaStreamWaitEvent(s.s_compute, rg.ready, 0));
-            a.series = (const R*)s.series + (size_t)rg.a0 * ctx->D * ctx->Tld;
+            a.series = (const R*)s.series + (size_t)rg.a0 * ctx->DS * ctx->Tld;
             a.by_particle = s.by_particle + (size_t)rg.a0 * ctx->Tld;
             a.natoms = (int)rg.n;
             kern<<<(int)std::min<int64_t>(grid, rg.n), nthr, dyn, s.s_compute>>>(a);
@@ -582,11 +583,11 @@ int launch_fft_fast_r1(ta_ctx* ctx, std::vector<int>* grids) {
         a.partial = s.partial;
         a.omega = (const cplx<RT>*)s.f_omega; a.tw2 = (const cplx<RT>*)s.f_tw2; a.map = s.f_map;
         a.wbase = (const cplx<RT>*)s.f_wbase; a.inv = (const RT*)s.f_inv;
-        a.D = ctx->D; a.T = (int)ctx->T; a.nh = (int)((ctx->T + 1) / 2); a.Tld = ctx->Tld;
+        a.D = ctx->D; a.DS = ctx->DS; a.T = (int)ctx->T; a.nh = (int)((ctx->T + 1) / 2); a.Tld = ctx->Tld;
         CK(cudaEventRecord(s.ev_ka, s.s_compute));
         for (const LaunchRange& rg : take_launch_ranges(s)) {
             if (rg.ready) CK(cudaStreamWaitEvent(s.s_compute, rg.ready, 0));
-            a.series = (const RT*)s.series + (size_t)rg.a0 * ctx->D * ctx->Tld;
+            a.series = (const RT*)s.series + (size_t)rg.a0 * ctx->DS * ctx->Tld;
             a.by_particle = s.by_particle + (size_t)rg.a0 * ctx->Tld;
             a.natoms = (int)rg.n;
             kern<<<(int)std::min<int64_t>(grid, rg.n), NT, smem, s.s_compute>>>(a);
@@ -658,13 +659,13 @@ int launch_windowed(ta_ctx* ctx, double denom, std::vector<int>* grids) {
         if (rc) return rc;
         WinArgs a;
         a.partial = s.partial;
-        a.D = ctx->D; a.T = T; a.Tld = ctx->Tld; a.denom = denom;
+        a.D = ctx->D; a.DS = ctx->DS; a.T = T; a.Tld = ctx->Tld; a.denom = denom;
         a.scratch = in_smem ? nullptr : (unsigned char*)s.win_scratch;
         a.scratch_stride = (long long)smem;
         CK(cudaEventRecord(s.ev_ka, s.s_compute));
         for (const LaunchRange& rg : take_launch_ranges(s)) {
             if (rg.ready) CK(cudaStreamWaitEvent(s.s_compute, rg.ready, 0));
-            a.series = (const R*)s.series + (size_t)rg.a0 * ctx->D * ctx->Tld;
+            a.series = (const R*)s.series + (size_t)rg.a0 * ctx->DS * ctx->Tld;
             a.by_particle = s.by_particle + (size_t)rg.a0 * ctx->Tld;
             a.natoms = (int)rg.n;
             if (in_smem) k_windowed<R, MODE, false><<<(int)std::min<int64_t>(grid, rg.n), nthr, dyn_smem, s.s_compute>>>(a);
@@ -867,6 +868,7 @@ int ta_stage_begin(ta_ctx* ctx, int64_t T, int64_t N, int D, const int* dims, in
     }
     free_problem(ctx);
     ctx->T = T; ctx->N = N; ctx->D = D;
+    ctx->DS = D + ((n_fields == 2 && precision == TA_PRECISION_FP64) ? 1 : 0);
     for (int i = 0; i < 3; ++i) ctx->dims[i] = (i < D) ? dims[i] : 0;
     ctx->src_dtype = src_dtype;
     ctx->elt = (src_dtype == TA_DTYPE_F32) ? 4 : 8;
@@ -893,7 +895,7 @@ int ta_stage_begin(ta_ctx* ctx, int64_t T, int64_t N, int D, const int* dims, in
         CK(cudaMalloc(&s.ts_sum, ((size_t)ctx->Tld + 16) * sizeof(double)));
         if (s.natoms == 0) continue;
         // the series are stored in the arithmetic type: double, or float in the FP32 mode
-        const size_t ser_bytes = (size_t)s.natoms * D * ctx->Tld * (precision == TA_PRECISION_FP64 ? sizeof(double) : sizeof(float));
+        const size_t ser_bytes = (size_t)s.natoms * ctx->DS * ctx->Tld * (precision == TA_PRECISION_FP64 ? sizeof(double) : sizeof(float));
         const size_t out_bytes = (size_t)s.natoms * ctx->Tld * sizeof(double);
         cudaError_t e = cudaMalloc(&s.series, ser_bytes);
         if (e == cudaSuccess) e = cudaMalloc(&s.by_particle, out_bytes);
@@ -1089,58 +1091,67 @@ int ta_helfand_fft(ta_ctx* ctx, const double* volumes, double boltzmann, double 
     // K5 / K6 keep T + 1 prefix sums in shared memory: refuse BEFORE the FFT pass runs, so that a caller that falls
     // back to ta_helfand has not paid for it
     for (auto& s : ctx->sh)
-        if (s.natoms > 0 && ((size_t)ctx->T + 1) * sizeof(double) > (size_t)s.max_smem)
+        if (s.natoms > 0 && ((size_t)ctx->Tld * sizeof(double) + 320 > (size_t)s.max_smem || ctx->T > 32768 || ctx->DS != ctx->D + 1))
             return fail(ctx, TA_ERR_UNSUPPORTED, "FFT Helfand route: T=" + std::to_string(ctx->T) + " does not fit shared memory");
     if ((rc = ensure_fft_plan(ctx))) return rc;
     std::vector<int> grids;
     if ((rc = launch_k1(ctx, &grids))) return rc;                 // by_particle = sum_d acf_d
-    // K5 forms S1 - 2 S2 and marks the lags whose result is not good to 1e-10 (cancellation); K6 evaluates those exactly and
-    // sums the particles.  thr = C eps / tol: C = 100 + T / 100 bounds the error constant of S1 - 2 S2 (FFT autocorrelation +
-    // prefix sums; measured 11 - 18 on random, random-walk and ramp moments, 15 at T = 3,000 and 33 at T = 10,000 on smooth
-    // ones: scripts/helfand_fft_error_constant.py), tol = 2e-11 leaves a factor 5 to the 1e-10 bar on top of that.
-    // If a shard has more than 2 % of its (particle, lag) pairs marked, the direct kernel K3 does that shard instead.
+    // K5 forms S1 - 2 S2 and lists the lags whose result is not good to 1e-10 (cancellation); K6 evaluates those exactly.
+    // thr = C eps / tol: C = 100 + T / 100 bounds the error constant of S1 - 2 S2 (FFT autocorrelation + prefix sums;
+    // measured 9 - 20 on random, random-walk, ramp, spike, offset and piecewise-constant moments, 18 - 33 on smooth ones:
+    // scripts/helfand_fft_error_constant.py -> profiles/r02_helfand_fft_error_constant.txt), tol = 2e-11 leaves a factor 5
+    // to the 1e-10 bar on top of that.  If more than 2 % of a shard's (particle, lag) pairs are listed -- or a warp's list
+    // overflows -- the direct kernel K3 does the whole call instead.
     const double thr = ctx->opt_helfand_thr >= -1.5 ? ctx->opt_helfand_thr
                                                     : (100.0 + (double)ctx->T / 100.0) * 1.1102230246251565e-16 / 2e-11;
-    const size_t smem = ((size_t)ctx->T + 1) * sizeof(double);
-    const int nwords = (int)((ctx->T + 31) / 32);
-    std::vector<unsigned long long> nflag(ctx->sh.size(), 0);
+    const size_t row_bytes = (size_t)ctx->Tld * sizeof(double);
+    std::vector<unsigned long long> totals(2 * ctx->sh.size(), 0);
+    std::vector<HelfandFftArgs> hargs(ctx->sh.size());
     for (size_t i = 0; i < ctx->sh.size(); ++i) {
         Shard& s = ctx->sh[i];
         if (s.natoms == 0) continue;
         CK(cudaSetDevice(s.dev));
-        if (smem > (size_t)s.max_smem)
-            return fail(ctx, TA_ERR_UNSUPPORTED, "FFT Helfand route: T=" + std::to_string(ctx->T) + " does not fit shared memory");
-        const size_t fbytes = (size_t)s.natoms * nwords * sizeof(uint32_t) + 16;
-        if (s.hflags_bytes < fbytes) {
+        // one q buffer per CTA; two CTAs per SM where two rows fit (T <= ~14,000): they cover each other's load latencies
+        // better than one CTA with the next row prefetched into a second buffer (7.3 against 11.0 ms at 125,000 x 10,000)
+        const bool two = 2 * (row_bytes + 320) <= (size_t)s.max_smem;
+        const int nbuf = 1;
+        const size_t smem = (size_t)nbuf * row_bytes;
+        auto k5 = two ? k5_helfand_fft_finish<2> : k5_helfand_fft_finish<1>;
+        CK(cudaFuncSetAttribute(k5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k5, K5_THREADS, smem));
+        if (occ < 1) return fail(ctx, TA_ERR_UNSUPPORTED, "K5 does not fit on an SM");
+        // one grid for K5 and K6: K6 walks the lists K5's warps wrote and corrects the per-CTA sum rows K5 formed
+        const int grid = (int)std::min<int64_t>(s.natoms, (int64_t)s.num_sms * occ);
+        grids[i] = grid;
+        if ((rc = ensure_partial(ctx, s, (size_t)grid))) return rc;    // zeroes the rows (K1's sums of the ACF are not wanted)
+        // lists: room for twice the 2 % of pairs at which K3 takes over, shared evenly by the grid's warps
+        const size_t nlists = (size_t)grid * K5_WARPS;
+        // ... and for up to four particles of a CTA that are marked at every lag (a spike, a particle at rest among moving ones)
+        const size_t per_cta = (size_t)((s.natoms + grid - 1) / grid);
+        const size_t cap = std::max((size_t)(0.04 * (double)s.natoms * (double)ctx->T / (double)nlists) + 64,
+                                    ((size_t)ctx->T / K5_WARPS + 1) * std::min<size_t>(per_cta, 4));
+        const size_t lbytes = nlists * cap * sizeof(unsigned long long) + nlists * sizeof(unsigned) + 64;
+        if (s.hflags_bytes < lbytes) {
             cudaFree(s.hflags);
             s.hflags = nullptr; s.hflags_bytes = 0;
-            CK(cudaMalloc((void**)&s.hflags, fbytes));
-            s.hflags_bytes = fbytes;
+            CK(cudaMalloc((void**)&s.hflags, lbytes));
+            s.hflags_bytes = lbytes;
         }
-        unsigned long long* counter = reinterpret_cast<unsigned long long*>(
-            reinterpret_cast<unsigned char*>(s.hflags) + ((fbytes - 16 + 7) & ~(size_t)7));
-        CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s.s_compute));
-        CK(cudaFuncSetAttribute(k5_helfand_fft_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaFuncSetAttribute(k6_helfand_refine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int occ = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k5_helfand_fft_finish, K5_THREADS, smem));
-        if (occ < 1) return fail(ctx, TA_ERR_UNSUPPORTED, "K5 does not fit on an SM");
-        int occ6 = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ6, k6_helfand_refine, K5_THREADS, smem));
-        if (occ6 < 1) return fail(ctx, TA_ERR_UNSUPPORTED, "K6 does not fit on an SM");
-        // one grid for K5 and K6: K6 corrects the per-CTA partial rows K5 wrote, with the same CTA -> particle map
-        const int grid = (int)std::min<int64_t>(s.natoms, (int64_t)s.num_sms * std::min(occ, occ6));
-        grids[i] = grid;
-        if ((rc = ensure_partial(ctx, s, (size_t)grid))) return rc;    // drops K1's partial rows (sums of the ACF)
-        HelfandFftArgs a;
+        HelfandFftArgs& a = hargs[i];
         a.series = (const double*)s.series; a.by_particle = s.by_particle; a.partial = s.partial;
-        a.natoms = (int)s.natoms; a.D = ctx->D; a.T = (int)ctx->T; a.Tld = ctx->Tld; a.denom = denom;
-        a.flags = s.hflags; a.nwords = nwords; a.nflagged = counter; a.thr = thr;
-        k5_helfand_fft_finish<<<grid, K5_THREADS, smem, s.s_compute>>>(a);
+        a.natoms = (int)s.natoms; a.D = ctx->D; a.DS = ctx->DS; a.T = (int)ctx->T; a.Tld = ctx->Tld; a.denom = denom;
+        unsigned char* base = reinterpret_cast<unsigned char*>(s.hflags);
+        a.total = reinterpret_cast<unsigned long long*>(base);                       // [2], then the lists, then the counts
+        a.list = reinterpret_cast<unsigned long long*>(base + 64);
+        a.count = reinterpret_cast<unsigned*>(base + 64 + nlists * cap * sizeof(unsigned long long));
+        a.cap = (unsigned)cap; a.thr = thr; a.nbuf = nbuf;
+        CK(cudaMemsetAsync(a.total, 0, 2 * sizeof(unsigned long long), s.s_compute));
+        k5<<<grid, K5_THREADS, smem, s.s_compute>>>(a);
         CK(cudaGetLastError());
         ctx->launches++;
         CK(cudaEventRecord(s.ev_kb, s.s_compute));                   // ta_last_kernel_ms: K1 + K5 (+ K6 below)
-        CK(cudaMemcpyAsync(&nflag[i], counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.s_compute));
+        CK(cudaMemcpyAsync(&totals[2 * i], a.total, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.s_compute));
     }
     bool need_k3 = false;
     ctx->helfand_fft_flagged = 0;
@@ -1149,8 +1160,8 @@ int ta_helfand_fft(ta_ctx* ctx, const double* volumes, double boltzmann, double 
         if (s.natoms == 0) continue;
         CK(cudaSetDevice(s.dev));
         CK(cudaStreamSynchronize(s.s_compute));
-        ctx->helfand_fft_flagged += (long long)nflag[i];
-        if ((double)nflag[i] > 0.02 * (double)s.natoms * (double)ctx->T) need_k3 = true;
+        ctx->helfand_fft_flagged += (long long)totals[2 * i];
+        if ((double)totals[2 * i] > 0.02 * (double)s.natoms * (double)ctx->T || totals[2 * i + 1] > 0) need_k3 = true;
     }
     if (need_k3) {
         // too much of the result needs the exact evaluation (series that barely move): the direct kernel does it all
@@ -1161,15 +1172,9 @@ int ta_helfand_fft(ta_ctx* ctx, const double* volumes, double boltzmann, double 
     }
     for (size_t i = 0; i < ctx->sh.size(); ++i) {
         Shard& s = ctx->sh[i];
-        if (s.natoms == 0) continue;
+        if (s.natoms == 0 || totals[2 * i] == 0) continue;           // nothing to correct on this shard
         CK(cudaSetDevice(s.dev));
-        if (nflag[i] == 0) continue;                                  // nothing to correct on this shard
-        const int grid = grids[i];
-        HelfandFftArgs a;
-        a.series = (const double*)s.series; a.by_particle = s.by_particle; a.partial = s.partial;
-        a.natoms = (int)s.natoms; a.D = ctx->D; a.T = (int)ctx->T; a.Tld = ctx->Tld; a.denom = denom;
-        a.flags = s.hflags; a.nwords = nwords; a.nflagged = nullptr; a.thr = thr;
-        k6_helfand_refine<<<grid, K5_THREADS, smem, s.s_compute>>>(a);
+        k6_helfand_refine<<<grids[i], K5_THREADS, 0, s.s_compute>>>(hargs[i]);
         CK(cudaGetLastError());
         ctx->launches++;
         CK(cudaEventRecord(s.ev_kb, s.s_compute));                   // ta_last_kernel_ms: K1 + K5 + K6

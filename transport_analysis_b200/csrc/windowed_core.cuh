@@ -137,10 +137,10 @@ TA_HD double win_reduce16(const R* acc, bool take, int lane) {
 }
 
 struct WinArgs {
-    const void* series;     // [natoms][D][Tld] of the arithmetic type R (double, or float in the FP32 mode)
+    const void* series;     // [natoms][DS][Tld] of the arithmetic type R (double, or float in the FP32 mode); rows 0 .. D-1 are used
     double* by_particle;    // [natoms][Tld]
     double* partial;        // [nblk][Tld]
-    int natoms, D, T;
+    int natoms, D, DS, T;
     long long Tld;
     double denom;           // Helfand: 2 kB <V> temp_avg ; VACF: unused
     // Series too long for shared memory: per-CTA global scratch (same layout, read through L1/L2) -- slower,
@@ -169,7 +169,7 @@ TA_HD void win_body(const WinArgs& A, unsigned char* smem_raw, int tid, int nthr
     for (int a = bid; a < A.natoms; a += nblk) {
         for (int k = tid; k < T; k += nthr) res[k] = 0.0;
         for (int d = 0; d < A.D; ++d) {
-            const R* ser = reinterpret_cast<const R*>(A.series) + ((size_t)a * A.D + d) * A.Tld;
+            const R* ser = reinterpret_cast<const R*>(A.series) + ((size_t)a * A.DS + d) * A.Tld;
             Ctx::sync();   // previous series fully consumed
             for (int x = tid; x < ne; x += nthr) S[x] = (R)0;
             Ctx::sync();
