@@ -64,24 +64,30 @@ static int run_fft(const double* series_f64, int T, int D, int Tld, int nthr, do
 }
 
 template <typename R>
-static int run_win(const double* series_f64, int T, int D, int Tld, int mode, int nwarps, double* res) {
+static int run_win(const double* series_f64, int T, int D, int Tld, int mode, int nwarps, int nsplit, double* res) {
     const std::vector<R> series_r = series_as<R>(series_f64, (size_t)D * Tld);
     const R* series = series_r.data();
-    // the kernel body itself (windowed_core.cuh win_body) for one particle, one CTA of nwarps warps;
-    // returns the un-normalised lag sums (row * (T - k) [* D * denom])
+    // the kernel body itself (windowed_core.cuh win_body) for one particle, CTAs of nwarps warps, one per part of the
+    // particle (nsplit); returns the un-normalised lag sums (row * (T - k) [* D * denom])
     const int ne = win_smem_elems(T);
     std::vector<unsigned char> smem((size_t)((ne + 1) & ~1) * sizeof(R) + (size_t)T * sizeof(double) + 64);
     unsigned char* sm = smem.data() + (16 - ((uintptr_t)smem.data() & 15)) % 16;
-    std::vector<double> row(Tld, 0.0), partial(Tld, 0.0);
+    const int nblk = nsplit;
+    std::vector<double> row(Tld, 0.0), partial((size_t)nblk * Tld, 0.0);
     WinArgs a;
     a.series = series; a.by_particle = row.data(); a.partial = partial.data();
     a.natoms = 1; a.D = D; a.DS = D; a.T = T; a.Tld = Tld; a.denom = 1.0;
-    a.scratch = nullptr; a.scratch_stride = 0;
+    a.scratch = nullptr; a.scratch_stride = 0; a.nsplit = nsplit;
     const int nthr = 32 * nwarps;
-    if (mode == TA_WIN_PRODUCT) emu::run_cta(nthr, [&](int tid) { win_body<R, TA_WIN_PRODUCT, emu::EmuCtx>(a, sm, tid, nthr, 0, 1); });
-    else emu::run_cta(nthr, [&](int tid) { win_body<R, TA_WIN_SQDIFF, emu::EmuCtx>(a, sm, tid, nthr, 0, 1); });
+    for (int bid = 0; bid < nblk; ++bid) {
+        if (mode == TA_WIN_PRODUCT) emu::run_cta(nthr, [&](int tid) { win_body<R, TA_WIN_PRODUCT, emu::EmuCtx>(a, sm, tid, nthr, bid, nblk); });
+        else emu::run_cta(nthr, [&](int tid) { win_body<R, TA_WIN_SQDIFF, emu::EmuCtx>(a, sm, tid, nthr, bid, nblk); });
+    }
     for (int k = 0; k < T; ++k) {
-        if (row[k] != partial[k]) return -2;
+        double psum = 0.0;                              // every lag is finished by exactly one CTA
+        int writers = 0;
+        for (int b = 0; b < nblk; ++b) { psum += partial[(size_t)b * Tld + k]; writers += partial[(size_t)b * Tld + k] != 0.0; }
+        if (row[k] != psum || writers > 1) return -2;
         res[k] = row[k] * (double)(T - k) * (mode == TA_WIN_PRODUCT ? 1.0 : (double)D);
     }
     return 0;
@@ -139,9 +145,9 @@ int emu_fft_acf(const double* series, int T, int D, int Tld, int nthr, int use_f
     return use_f32 ? run_fft<float>(series, T, D, Tld, nthr, row, partial)
                    : run_fft<double>(series, T, D, Tld, nthr, row, partial);
 }
-int emu_windowed(const double* series, int T, int D, int Tld, int mode, int nwarps, int use_f32, double* res) {
-    return use_f32 ? run_win<float>(series, T, D, Tld, mode, nwarps, res)
-                   : run_win<double>(series, T, D, Tld, mode, nwarps, res);
+int emu_windowed(const double* series, int T, int D, int Tld, int mode, int nwarps, int nsplit, int use_f32, double* res) {
+    return use_f32 ? run_win<float>(series, T, D, Tld, mode, nwarps, nsplit, res)
+                   : run_win<double>(series, T, D, Tld, mode, nwarps, nsplit, res);
 }
 int emu_plan(int T, int* H, int* npasses, int* radix) {
     FftPlanHost hp;

@@ -29,13 +29,13 @@ def emu_fft(lib, x, nthr=96, f32=0):
     return row[:T]
 
 
-def emu_win(lib, x, mode, nwarps=4, f32=0):
+def emu_win(lib, x, mode, nwarps=4, f32=0, nsplit=1):
     T, D = x.shape
     Tld = (T + 15) // 16 * 16
     ser = np.zeros((D, Tld))
     ser[:, :T] = x.T
     res = np.zeros(T)
-    assert lib.emu_windowed(_p(ser), T, D, Tld, mode, nwarps, f32, _p(res)) == 0
+    assert lib.emu_windowed(_p(ser), T, D, Tld, mode, nwarps, nsplit, f32, _p(res)) == 0
     return res
 
 
@@ -75,6 +75,17 @@ def test_windowed_phases(emu, T):
         got = emu_win(emu, x, 1, nwarps)
         assert got[0] == 0.0
         np.testing.assert_allclose(got, sq, rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize("T,nwarps,nsplit", [(100, 1, 2), (333, 2, 3), (1000, 4, 2), (1000, 2, 7), (2000, 16, 4), (17, 1, 4)])
+def test_windowed_particle_split_over_ctas(emu, T, nwarps, nsplit):
+    """A particle's lag-block pairs dealt to nsplit CTAs (few-particle workloads): every lag is finished by exactly one
+    of them, and the values are those of the one-CTA run bit for bit."""
+    x = np.random.default_rng(T + nsplit).standard_normal((T, 2)) + 0.5
+    for mode in (0, 1):
+        one = emu_win(emu, x, mode, nwarps)
+        split = emu_win(emu, x, mode, nwarps, nsplit=nsplit)
+        assert np.array_equal(one, split)
 
 
 def test_fp32_mode_tolerance(emu):

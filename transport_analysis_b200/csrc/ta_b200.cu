@@ -644,7 +644,13 @@ int launch_windowed(ta_ctx* ctx, double denom, std::vector<int>* grids) {
         if (in_smem) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_windowed<R, MODE, false>, nthr, dyn_smem));
         else occ = 1;
         if (occ < 1) return fail(ctx, TA_ERR_UNSUPPORTED, "windowed kernel does not fit on an SM");
-        int grid = (int)std::min<int64_t>(s.natoms, (int64_t)s.num_sms * occ);
+        // fewer than four particles per resident CTA: deal each particle's lag-block pairs to several CTAs, so that the
+        // last wave of the grid is full (BASELINE configs[1]: 1,000 particles on 592 resident CTAs)
+        const int64_t resident = (int64_t)s.num_sms * occ;
+        const int max_split = std::max(1, npairs / std::max(1, nthr / 32));
+        const int nsplit = (in_smem && s.natoms < 4 * resident)
+                               ? (int)std::max<int64_t>(1, std::min<int64_t>(max_split, (4 * resident + s.natoms - 1) / s.natoms)) : 1;
+        int grid = (int)std::min<int64_t>(s.natoms * nsplit, resident);
         if (!in_smem) {
             const size_t need = smem * (size_t)grid;
             if (s.win_scratch_bytes < need) {
@@ -662,13 +668,14 @@ int launch_windowed(ta_ctx* ctx, double denom, std::vector<int>* grids) {
         a.D = ctx->D; a.DS = ctx->DS; a.T = T; a.Tld = ctx->Tld; a.denom = denom;
         a.scratch = in_smem ? nullptr : (unsigned char*)s.win_scratch;
         a.scratch_stride = (long long)smem;
+        a.nsplit = nsplit;
         CK(cudaEventRecord(s.ev_ka, s.s_compute));
         for (const LaunchRange& rg : take_launch_ranges(s)) {
             if (rg.ready) CK(cudaStreamWaitEvent(s.s_compute, rg.ready, 0));
             a.series = (const R*)s.series + (size_t)rg.a0 * ctx->DS * ctx->Tld;
             a.by_particle = s.by_particle + (size_t)rg.a0 * ctx->Tld;
             a.natoms = (int)rg.n;
-            if (in_smem) k_windowed<R, MODE, false><<<(int)std::min<int64_t>(grid, rg.n), nthr, dyn_smem, s.s_compute>>>(a);
+            if (in_smem) k_windowed<R, MODE, false><<<(int)std::min<int64_t>(grid, rg.n * nsplit), nthr, dyn_smem, s.s_compute>>>(a);
             else k_windowed<R, MODE, true><<<(int)std::min<int64_t>(grid, rg.n), nthr, 0, s.s_compute>>>(a);
             CK(cudaGetLastError());
             ctx->launches++;

@@ -147,10 +147,15 @@ struct WinArgs {
     // but the direct lag sums then work for any T.  Null: the series and the lag sums live in shared memory.
     unsigned char* scratch;
     long long scratch_stride;   // bytes per CTA
+    // Few particles (fewer than ~4 per resident CTA): a particle's lag-block pairs are dealt to `nsplit` CTAs, each of which
+    // stages the whole series but computes, finishes and stores only the lags of its own pairs -- the work units
+    // (particle, part) are then small enough to fill the last wave of the grid.  1: a CTA does a whole particle.
+    int nsplit;
 };
 
 // ---------------------------------------------------------------------------
-// The kernel body for one CTA (persistent over particles bid, bid + nblk, ...).  Ctx supplies
+// The kernel body for one CTA (persistent over work units bid, bid + nblk, ...; unit u = part u % nsplit of particle
+// u / nsplit).  Ctx supplies
 // sync() and shfl_xor(); tests/emu runs the same code on the CPU under cooperative fibers.
 //   MODE = TA_WIN_PRODUCT: vacf[k] = sum_d sum_i g_d[i] g_d[i+k] / (T-k)
 //   MODE = TA_WIN_SQDIFF : visc[k] = sum_d sum_i (g_d[i]-g_d[i+k])^2 / (D (T-k)) / denom
@@ -166,7 +171,11 @@ TA_HD void win_body(const WinArgs& A, unsigned char* smem_raw, int tid, int nthr
     const int nlb = win_num_lag_blocks(T), npairs = win_num_pairs(nlb);
     double* partial = A.partial + (size_t)bid * A.Tld;
 
-    for (int a = bid; a < A.natoms; a += nblk) {
+    const int nsplit = A.nsplit > 1 ? A.nsplit : 1;
+    // lag block blk belongs to pair min(blk, nlb - 1 - blk); pair p is computed by part (p / nwarps) % nsplit
+    auto part_of = [&](int blk) { const int p = blk < nlb - 1 - blk ? blk : nlb - 1 - blk; return (p / nwarps) % nsplit; };
+    for (long long u = bid; u < (long long)A.natoms * nsplit; u += nblk) {
+        const int a = (int)(u / nsplit), part = (int)(u % nsplit);
         for (int k = tid; k < T; k += nthr) res[k] = 0.0;
         for (int d = 0; d < A.D; ++d) {
             const R* ser = reinterpret_cast<const R*>(A.series) + ((size_t)a * A.DS + d) * A.Tld;
@@ -176,7 +185,7 @@ TA_HD void win_body(const WinArgs& A, unsigned char* smem_raw, int tid, int nthr
             for (int x = tid; x < T; x += nthr) S[win_addr(x)] = ser[x];
             Ctx::sync();
             // ---- unmasked tiles: a warp per block pair, lanes split between the two blocks
-            for (int pair = warp; pair < npairs; pair += nwarps) {
+            for (int pair = part * nwarps + warp; pair < npairs; pair += nwarps * nsplit) {
                 int ka, kb;
                 win_pair_blocks(pair, nlb, &ka, &kb);
                 const int nfa = win_full_chunks<MODE>(T, ka);
@@ -204,6 +213,7 @@ TA_HD void win_body(const WinArgs& A, unsigned char* smem_raw, int tid, int nthr
                 // ---- masked tail tiles: one lane per lag block (no cross-lane reduction, fixed order)
                 Ctx::sync();
                 for (int blk = tid; blk < nlb; blk += nthr) {
+                    if (nsplit > 1 && part_of(blk) != part) continue;
                     const int k0 = blk * TA_WIN_LAGS;
                     R acc[TA_WIN_LAGS];
 #pragma unroll
@@ -220,6 +230,7 @@ TA_HD void win_body(const WinArgs& A, unsigned char* smem_raw, int tid, int nthr
         Ctx::sync();
         double* row = A.by_particle + (size_t)a * A.Tld;
         for (int k = tid; k < T; k += nthr) {
+            if (nsplit > 1 && part_of(k / TA_WIN_LAGS) != part) continue;      // another CTA finishes this lag
             double val;
             if (MODE == TA_WIN_PRODUCT) val = res[k] / (double)(T - k);
             else val = res[k] / ((double)A.D * (double)(T - k)) / A.denom;
