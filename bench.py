@@ -347,8 +347,10 @@ def run_reference(args, rank, world):
     emit(json.dumps(line))
 
 
-def workload_config(workload, A, T, gpus):
-    spec = WORKLOADS.get(workload, {})
+def workload_config(workload, A, T, gpus, cfg=None):
+    spec = dict(WORKLOADS.get(workload, {}))
+    if cfg:
+        spec["cfg"] = cfg
     kind = kind_of(workload)
     bytes_in = A * T * 12 * (2 if kind.startswith("helfand") else 1)
     return {"workload": f"{NAMES[kind]} (BASELINE.json {spec.get('cfg', 'custom size')})", "atoms_per_gpu": A,
@@ -495,7 +497,7 @@ def parity_check(env, kind, precision, ana, vel, pos, masses, T, A, check_lag0=T
 
 
 def measure(env, name, kind, A, T, precision, steps, warmup, vel, pos=None, staging="auto", e2e_steps=None,
-            with_cpu_baseline=False, device_leg=True, check_lag0=True, note=None):
+            with_cpu_baseline=False, device_leg=True, check_lag0=True, note=None, cfg=None):
     """One workload: e2e through the public class (cold first run, then warm steps), the device-resident compute
     call, parity evidence, roofline.  Returns the record (rank 0 fills in the rank-independent parts)."""
     from transport_analysis_b200.synthetic import make_universe
@@ -578,7 +580,7 @@ def measure(env, name, kind, A, T, precision, steps, warmup, vel, pos=None, stag
         return rec
     bpa = (BYTES_PER_AF if precision == "fp64" else BYTES_PER_AF_FP32)[kind]
     rec.update({
-        "config": dict(workload_config(name if name in WORKLOADS else kind, A, T, world), staging=staging),
+        "config": dict(workload_config(name if name in WORKLOADS else kind, A, T, world, cfg), staging=staging),
         "e2e": {"value": af_total / (e2e_ms / 1e3), "unit": "atom-frames/s", "ms_per_step": e2e_ms,
                 "cold_ms_first_run": cold_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "h2d_gbs_per_gpu": h2d / (e2e_ms / 1e3) / 1e9, "api": API[kind] + ("" if precision == "fp64" else " with precision='fp32'"),
@@ -704,12 +706,17 @@ def run_b200(args, rank, world, local_rank):
             else:
                 v5 = synthetic_trajectory(T5, A5, seed=777 + rank)
                 cfg5_note = "BASELINE.json configs[4]: 1,000,000 atoms x 10,000 frames, atoms sharded over the ranks, one NCCL all-reduce"
-                sub("cfg5_vacf_fft", kind="fft", A=A5, T=T5, precision="fp64", steps=3, warmup=1, vel=v5, e2e_steps=1, note=cfg5_note)
+                sub("cfg5_vacf_fft", kind="fft", A=A5, T=T5, precision="fp64", steps=3, warmup=1, vel=v5, e2e_steps=1, note=cfg5_note,
+                    cfg="configs[4]")
                 # the same array serves as positions (g = m v v): no second 15 - 60 GB host array
-                sub("cfg5_helfand_fft", kind="helfand_fft", A=A5, T=T5, precision="fp64", steps=2, warmup=1, vel=v5, pos=v5,
-                    e2e_steps=1, note=cfg5_note + "; opt-in O(T log T) route")
-                sub("cfg5_helfand", kind="helfand_direct", A=A5, T=T5, precision="fp64", steps=1, warmup=0, vel=v5, pos=v5,
-                    e2e_steps=0, note=cfg5_note + "; default direct route (O(T^2))")
+                need_helf = A5 * T5 * 40 + (2 << 30)          # four series rows (g_x, g_y, g_z, sum g^2) + the per-particle rows
+                if need_helf > 178e9:
+                    workloads["cfg5_helfand"] = {"skipped": f"{A5} atoms per GPU need {need_helf / 1e9:.0f} GB of HBM for the Helfand series + results"}
+                else:
+                    sub("cfg5_helfand_fft", kind="helfand_fft", A=A5, T=T5, precision="fp64", steps=2, warmup=1, vel=v5, pos=v5,
+                        e2e_steps=1, note=cfg5_note + "; opt-in O(T log T) route", cfg="configs[4]")
+                    sub("cfg5_helfand", kind="helfand_direct", A=A5, T=T5, precision="fp64", steps=1, warmup=0, vel=v5, pos=v5,
+                        e2e_steps=0, note=cfg5_note + "; default direct route (O(T^2))", cfg="configs[4]")
                 for k in ("cfg5_vacf_fft", "cfg5_helfand_fft", "cfg5_helfand"):
                     r = workloads.get(k, {})
                     if "roofline" in r:
