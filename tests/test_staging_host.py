@@ -155,3 +155,74 @@ def test_green_kubo_helpers_follow_the_reference(fake):
     assert a.self_diffusivity_gk_odd(stop=39) == pytest.approx(integrate.simpson(y=ts[:39], x=t[:39]) / 2)
     with pytest.raises(RuntimeError):
         VACF(u.atoms).self_diffusivity_gk()
+
+
+# ------------------------------------------------------------------ when the whole-trajectory path may be taken
+def test_bulk_path_from_an_explicit_regular_frame_list(fake):
+    """MDAnalysis >= 2.8 hands _setup_frames an explicit frame list (start / stop / step are then None): a regular list is
+    still streamed as a whole, an irregular one goes frame by frame."""
+    vel, _ = traj(T=20, N=4)
+    u = make_universe(None, vel)
+    a = VACF(u.atoms, fft=True).run(frames=[3, 8, 13])
+    assert a.start is None and ("bulk", [(20, 4, 3)], 0, 3, 5, 3) in fake.calls and "commit" not in names(fake)
+
+
+def test_per_frame_path_for_an_irregular_frame_list(fake):
+    vel, _ = traj(T=20, N=4)
+    u = make_universe(None, vel)
+    VACF(u.atoms, fft=True).run(frames=[3, 4, 9])
+    assert "bulk" not in names(fake)
+    commits = [c for c in fake.calls if c[0] == "commit"]
+    np.testing.assert_array_equal(np.concatenate([c[3][:, 0] for c in commits]), vel[[3, 4, 9]])
+
+
+def test_no_bulk_path_under_on_the_fly_transformations_or_on_request(fake):
+    """Transformations act on Timesteps, which the whole-trajectory path never builds; staging='per_frame' asks for the
+    _single_frame path outright."""
+    vel, _ = traj(T=6, N=3)
+    u = make_universe(None, vel)
+    u.trajectory.transformations = (lambda ts: ts,)
+    VACF(u.atoms, fft=True).run()
+    assert "bulk" not in names(fake) and names(fake).count("commit") == 2
+    FakeContext.created = []
+    u2 = make_universe(None, vel)
+    VACF(u2.atoms, fft=True, staging="per_frame").run()
+    assert "bulk" not in names(fake)
+    with pytest.raises(ValueError, match="staging"):
+        VACF(u2.atoms, staging="sometimes")
+
+
+def test_regular_frame_window_and_gather_index():
+    class A:
+        pass
+
+    a = A()
+    a.n_frames, a.start, a.step = 4, 2, 3
+    assert _staging.regular_frame_window(a) == (2, 3)
+    a.step = -1
+    assert _staging.regular_frame_window(a) is None
+    a.start = a.step = None
+    a._sliced_trajectory = type("S", (), {"_frames": [5, 7, 9, 11]})()
+    assert _staging.regular_frame_window(a) == (5, 2)
+    a._sliced_trajectory = type("S", (), {"frames": np.array([5, 7, 10, 11])})()
+    assert _staging.regular_frame_window(a) is None
+    a._sliced_trajectory = None
+    assert _staging.regular_frame_window(a) is None
+    assert _staging.gather_index(np.arange(3, 9)) == slice(3, 9)
+    ix = _staging.gather_index([4, 2, 7])
+    assert isinstance(ix, np.ndarray) and list(ix) == [4, 2, 7]
+    src, out = np.arange(30.0).reshape(10, 3), np.empty((3, 3))
+    _staging._gather(src, ix, out)
+    np.testing.assert_array_equal(out, src[[4, 2, 7]])
+    out6 = np.empty((6, 3))
+    _staging._gather(src, slice(3, 9), out6)
+    np.testing.assert_array_equal(out6, src[3:9])
+
+
+def test_against_a_real_mdanalysis_memory_reader(fake):
+    """With MDAnalysis installed the same classes sit on the real AnalysisBase / MemoryReader (not available in this image)."""
+    pytest.importorskip("MDAnalysis")
+    vel, pos = traj(T=12, N=5)
+    u = make_universe(pos, vel, masses=np.ones(5), dimensions=[10, 10, 10, 90, 90, 90])
+    VACF(u.atoms, fft=True).run(start=2, stop=11, step=3)
+    assert any(c[0] == "bulk" and c[3:] == (2, 3, 3) for c in fake.calls) or "commit" in names(fake)
