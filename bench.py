@@ -778,7 +778,7 @@ def main():
             port = os.environ.get("MASTER_PORT", "29511")
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                    "--master-addr", "127.0.0.1", "--master-port", port, os.path.abspath(__file__)] + sys.argv[1:]
-            sys.exit(subprocess.call(cmd))
+            sys.exit(subprocess.call(cmd, stdout=_REAL_STDOUT))      # the ranks' stdout is the real one, not the stderr alias
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     run_b200(args, rank, world, local_rank)
 

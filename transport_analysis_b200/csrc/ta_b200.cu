@@ -6,6 +6,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -647,9 +648,18 @@ int launch_windowed(ta_ctx* ctx, double denom, std::vector<int>* grids) {
         // fewer than four particles per resident CTA: deal each particle's lag-block pairs to several CTAs, so that the
         // last wave of the grid is full (BASELINE configs[1]: 1,000 particles on 592 resident CTAs)
         const int64_t resident = (int64_t)s.num_sms * occ;
-        const int max_split = std::max(1, npairs / std::max(1, nthr / 32));
-        const int nsplit = (in_smem && s.natoms < 4 * resident)
-                               ? (int)std::max<int64_t>(1, std::min<int64_t>(max_split, (4 * resident + s.natoms - 1) / s.natoms)) : 1;
+        const int nwarps = std::max(1, nthr / 32);
+        const int max_split = std::max(1, (npairs + nwarps - 1) / nwarps);      // every part keeps at least one round of pairs
+        int nsplit = 1;
+        if (in_smem && s.natoms < 4 * resident) {
+            // the split whose last wave is fullest (each part re-stages the series: ~2 % per extra part)
+            double best = 1e30;
+            for (int ns = 1; ns <= max_split; ++ns) {
+                const double units = (double)s.natoms * ns, waves = std::ceil(units / (double)resident);
+                const double cost = waves * (double)resident / units * (1.0 + 0.02 * (ns - 1));
+                if (cost < best - 1e-9) { best = cost; nsplit = ns; }
+            }
+        }
         int grid = (int)std::min<int64_t>(s.natoms * nsplit, resident);
         if (!in_smem) {
             const size_t need = smem * (size_t)grid;
