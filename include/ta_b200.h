@@ -119,6 +119,16 @@ int ta_helfand_fft(ta_ctx* ctx, const double* volumes /*[T]*/, double boltzmann,
                    double* ts_out);
 int ta_fetch_by_particle(ta_ctx* ctx, int64_t atom0, int64_t natoms, int layout, double* out);
 
+/* Post-processing of the atom-mean timeseries of the LAST compute call, which stays on the device:
+ * over the points w = start, start + step, ... < stop of (times[w], timeseries[w])
+ *   *integral  trapezoid rule           self_diffusivity_gk before its / dim_fac   velocityautocorr.py:316-322
+ *   running[n] running trapezoid integral, running[0] = initial (NULL: not wanted)  plot_running_integral :407-414
+ *   *slope     least-squares slope of the timeseries over times                      the fit of viscosity.py:235-245
+ * times[T] is a host array (the caller's self.times, or lag times for the fit).  Any of the three outputs may be NULL.
+ * The Simpson variant (self_diffusivity_gk_odd, :354-360) stays on the host with scipy. */
+int ta_green_kubo(ta_ctx* ctx, const double* times, int64_t start, int64_t stop, int64_t step, double initial,
+                  double* integral, double* running, double* slope);
+
 /* Device-side timing of whatever is enqueued between begin and end (CUDA
  * events on every shard's compute stream; ms = max over local devices). */
 int ta_timer_begin(ta_ctx* ctx);

@@ -177,6 +177,38 @@ def test_notebook_helfand_t10(route):
     assert_allclose(VH(u.atoms, fft=route).run().results.timeseries * 3, oracle.NOTEBOOK_HELFAND_T10_SUMDIMS, rtol=1e-10)
 
 
+# ------------------------------------------------------------------ device-side Green-Kubo / fit (kernel K7)
+def test_green_kubo_and_linear_fit_on_the_device(rand_u):
+    """postprocess='device': trapezoid integral, running integral and the least-squares slope are computed on the GPU from
+    the timeseries that is still there; against the reference's scipy / numpy calls on the host timeseries."""
+    from scipy import integrate
+
+    u, vel, pos, masses = rand_u
+    host = VACF(u.atoms, fft=True).run()
+    dev = VACF(u.atoms, fft=True, postprocess="device").run()
+    assert np.array_equal(host.results.timeseries, dev.results.timeseries)
+    for kw in ({}, {"start": 2, "stop": 100, "step": 3}, {"start": 5, "stop": 0, "step": 1}, {"start": 0, "stop": 699, "step": 2}):
+        assert_allclose(dev.self_diffusivity_gk(**kw), host.self_diffusivity_gk(**kw), rtol=1e-12)
+        t_d, r_d = dev.running_integral(initial=0.25, **kw)
+        t_h, r_h = host.running_integral(initial=0.25, **kw)
+        assert_allclose(t_d, t_h)
+        assert_allclose(r_d, r_h, rtol=1e-12, atol=1e-13 * np.abs(r_h).max())
+    assert_allclose(dev.self_diffusivity_gk_odd(stop=699), host.self_diffusivity_gk_odd(stop=699), rtol=1e-13)   # host both
+    # a timeseries longer than one scan tile of K7 (1,024 points)
+    v2, _ = random_trajectory(2500, 3, seed=4, rho=0.95)
+    d2 = VACF(make_universe(None, v2).atoms, postprocess="device").run()
+    want = integrate.trapezoid(d2.results.timeseries, d2.times) / 3
+    assert_allclose(d2.self_diffusivity_gk(), want, rtol=1e-12)
+    assert_allclose(d2.running_integral()[1], integrate.cumulative_trapezoid(d2.results.timeseries, d2.times, initial=0) / 3,
+                    rtol=1e-12, atol=1e-13)
+    for window in ((5, 30), (20, 650), (0, 699)):
+        h_host = VH(u.atoms, linear_fit_window=window).run()
+        h_dev = VH(u.atoms, linear_fit_window=window, postprocess="device").run()
+        assert_allclose(h_dev.results.viscosity, h_host.results.viscosity, rtol=1e-10)
+    with pytest.raises(ValueError, match="postprocess"):
+        VACF(u.atoms, postprocess="nowhere")
+
+
 # ------------------------------------------------------------------ C ABI direct
 def test_c_abi_f64_source_lag_major_and_errors():
     rng = np.random.default_rng(21)

@@ -41,6 +41,8 @@ _SIGNATURES = {
     "ta_helfand": (c_int, [c_void_p, POINTER(c_double), c_double, c_double, POINTER(c_double)]),
     "ta_helfand_fft": (c_int, [c_void_p, POINTER(c_double), c_double, c_double, POINTER(c_double)]),
     "ta_fetch_by_particle": (c_int, [c_void_p, c_int64, c_int64, c_int, POINTER(c_double)]),
+    "ta_green_kubo": (c_int, [c_void_p, POINTER(c_double), c_int64, c_int64, c_int64, c_double, POINTER(c_double),
+                              POINTER(c_double), POINTER(c_double)]),
     "ta_timer_begin": (c_int, [c_void_p]),
     "ta_timer_end": (c_int, [c_void_p, POINTER(c_float)]),
     "ta_last_kernel_ms": (c_int, [c_void_p, POINTER(c_float)]),
@@ -247,6 +249,21 @@ class Context:
         self._check(self._lib.ta_fetch_by_particle(self._h, int(atom0), int(natoms), TA_LAYOUT_ATOM_MAJOR,
                                                    _dptr(out)), "ta_fetch_by_particle")
         return out.T
+
+    def green_kubo(self, times, start=0, stop=None, step=1, initial=0.0, running=False):
+        """Trapezoid integral, least-squares slope and (optionally) running integral of the device-resident atom-mean
+        timeseries over ``times[start:stop:step]`` (kernel K7).  Returns ``(integral, slope, running | None)``."""
+        t = np.ascontiguousarray(times, dtype=np.float64)
+        if t.shape != (self.T,):
+            raise ValueError("times must have one entry per analysed frame")
+        stop = self.T if stop is None else int(stop)
+        n = len(range(int(start), stop, int(step)))
+        integ, slope = c_double(), c_double()
+        run = np.empty(n, dtype=np.float64) if running else None
+        self._check(self._lib.ta_green_kubo(self._h, _dptr(t), int(start), stop, int(step), float(initial),
+                                            ctypes.byref(integ), _dptr(run) if running else None, ctypes.byref(slope)),
+                    "ta_green_kubo")
+        return float(integ.value), float(slope.value), run
 
     # -- timing / introspection -------------------------------------------
     def timer_begin(self):

@@ -531,6 +531,84 @@ __global__ void k_sum_partials(const double* __restrict__ partial, int nrows, lo
     out[k] = s;
 }
 
+// K4c: the atom mean itself, on the device: mean[k] = sum[k] / count (count = the all-reduced particle number in slot Tld)
+__global__ void k_atom_mean(const double* __restrict__ ts_sum, long long Tld, int T, double* __restrict__ mean) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < T) mean[k] = ts_sum[k] / ts_sum[Tld];
+}
+
+// ---------------------------------------------------------------------------
+// K7: Green-Kubo post-processing of the device-resident atom-mean timeseries: trapezoid integral and
+// running integral of y[w] over x[w], w = start, start + step, ... (n points) -- what self_diffusivity_gk
+// (velocityautocorr.py:316-322) and plot_running_integral (:407-414) compute with scipy.integrate -- and the
+// least-squares slope of y over x (the linear fit of viscosity.py:235-245).  One CTA; O(T).
+//   out[0] = integral, out[1] = slope; running[0] = initial, running[i] = sum of the first i trapezoids (may be null)
+// ---------------------------------------------------------------------------
+constexpr int K7_THREADS = 1024;
+__global__ void __launch_bounds__(K7_THREADS)
+k7_green_kubo(const double* __restrict__ y, const double* __restrict__ x, long long start, long long step, int n,
+              double initial, double* __restrict__ running, double* __restrict__ out) {
+    __shared__ double wtot[K7_THREADS / 32];
+    __shared__ double carry_s;
+    __shared__ double red[2][K7_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry_s = 0.0;
+    if (running && tid == 0 && n > 0) running[0] = initial;
+    __syncthreads();
+    // trapezoids i = 0 .. n-2 in tiles of K7_THREADS, block scan per tile
+    for (int i0 = 0; i0 < n - 1; i0 += K7_THREADS) {
+        const int i = i0 + tid;
+        double t = 0.0;
+        if (i < n - 1) {
+            const long long a = start + (long long)i * step, b = a + step;
+            t = 0.5 * (x[b] - x[a]) * (y[b] + y[a]);
+        }
+        double v = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double u = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += u;
+        }
+        if (lane == 31) wtot[warp] = v;
+        __syncthreads();
+        double off = carry_s;
+        for (int w = 0; w < warp; ++w) off += wtot[w];
+        v += off;
+        if (running && i < n - 1) running[i + 1] = v;
+        __syncthreads();
+        if (tid == K7_THREADS - 1) carry_s = v;
+        __syncthreads();
+    }
+    // least squares of y over x: two passes (means, then centred sums), every sum in a fixed order
+    auto block_sum2 = [&](double a, double b, double* ra, double* rb) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+        __syncthreads();
+        if (lane == 0) { red[0][warp] = a; red[1][warp] = b; }
+        __syncthreads();
+        double sa = 0.0, sb = 0.0;
+        for (int w = 0; w < K7_THREADS / 32; ++w) { sa += red[0][w]; sb += red[1][w]; }
+        *ra = sa; *rb = sb;
+    };
+    double sx = 0.0, sy = 0.0;
+    for (int i = tid; i < n; i += K7_THREADS) { const long long a = start + (long long)i * step; sx += x[a]; sy += y[a]; }
+    double mx, my;
+    block_sum2(sx, sy, &mx, &my);
+    mx /= (double)(n > 0 ? n : 1); my /= (double)(n > 0 ? n : 1);
+    double sxx = 0.0, sxy = 0.0;
+    for (int i = tid; i < n; i += K7_THREADS) {
+        const long long a = start + (long long)i * step;
+        const double dx = x[a] - mx;
+        sxx += dx * dx; sxy += dx * (y[a] - my);
+    }
+    double txx, txy;
+    block_sum2(sxx, sxy, &txx, &txy);
+    if (tid == 0) {
+        out[0] = carry_s;
+        out[1] = (n >= 2 && txx != 0.0) ? txy / txx : 0.0;
+    }
+}
+
 // K4b: lag-major view of the per-particle result for a range of atoms:
 // out[k][j] = by_particle[atom0 + j][k]   (reference layout, velocityautocorr.py:145-147)
 __global__ void k_to_lag_major(const double* __restrict__ by_particle, long long Tld, int T,

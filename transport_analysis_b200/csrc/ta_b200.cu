@@ -94,6 +94,7 @@ struct Shard {
     double* by_particle = nullptr;
     double* masses = nullptr;
     double* ts_sum = nullptr;
+    double* ts_mean = nullptr;          // [Tld] atom mean of the last compute call (first shard only); + scratch of ta_green_kubo
     double* partial = nullptr;
     size_t partial_rows = 0;
     void* dstage[kNumDevStage][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
@@ -163,7 +164,7 @@ struct ta_ctx {
     int64_t opt_bulk_chunk = 0;
     double opt_helfand_thr = -2.0;       // < -1.5: the built-in rule
     int k1_threads = 0, k1_smem = 0, k1_grid = 0;
-    std::vector<double> host_ts;
+    bool have_mean = false;  // ts_mean of the first shard holds the result of a compute call
     int64_t launches = 0;
     long long helfand_fft_flagged = 0;   // (particle, lag) pairs the last ta_helfand_fft evaluated exactly; -1: all (K3 took over)
 };
@@ -199,6 +200,7 @@ void free_problem(ta_ctx* c) {
         cudaFree(s.by_particle); s.by_particle = nullptr;
         cudaFree(s.masses); s.masses = nullptr;
         cudaFree(s.ts_sum); s.ts_sum = nullptr;
+        cudaFree(s.ts_mean); s.ts_mean = nullptr;
         cudaFree(s.partial); s.partial = nullptr; s.partial_rows = 0;
         cudaFree(s.lagmajor_tmp); s.lagmajor_tmp = nullptr; s.lagmajor_bytes = 0;
         cudaFree(s.win_scratch); s.win_scratch = nullptr; s.win_scratch_bytes = 0;
@@ -229,6 +231,7 @@ void free_problem(ta_ctx* c) {
         c->slab_used[i] = false;
     }
     c->begun = false;
+    c->have_mean = false;
     c->plan_T = -1;
     c->frames_staged = 0;
     c->cur_slab = -1;
@@ -381,14 +384,16 @@ int finish_timeseries(ta_ctx* ctx, const std::vector<int>& grids, double* ts_out
         }
         CKN(g_nccl.GroupEnd());
     }
+    // the atom mean is formed on the device (it stays there for ta_green_kubo) and copied out
     Shard& s0 = ctx->sh[0];
-    ctx->host_ts.resize(cnt);
     CK(cudaSetDevice(s0.dev));
-    CK(cudaMemcpyAsync(ctx->host_ts.data(), s0.ts_sum, cnt * sizeof(double), cudaMemcpyDeviceToHost, s0.s_compute));
+    k_atom_mean<<<(T + 255) / 256, 256, 0, s0.s_compute>>>(s0.ts_sum, ctx->Tld, T, s0.ts_mean);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    CK(cudaMemcpyAsync(ts_out, s0.ts_mean, (size_t)T * sizeof(double), cudaMemcpyDeviceToHost, s0.s_compute));
     int rc = sync_all(ctx);
     if (rc) return rc;
-    const double ntot = ctx->host_ts[ctx->Tld];
-    for (int k = 0; k < T; ++k) ts_out[k] = ctx->host_ts[k] / ntot;
+    ctx->have_mean = true;
     return TA_OK;
 }
 
@@ -910,6 +915,7 @@ int ta_stage_begin(ta_ctx* ctx, int64_t T, int64_t N, int D, const int* dims, in
         s.stage_toggle = 0;
         CK(cudaSetDevice(s.dev));
         CK(cudaMalloc(&s.ts_sum, ((size_t)ctx->Tld + 16) * sizeof(double)));
+        CK(cudaMalloc(&s.ts_mean, (3 * (size_t)ctx->Tld + 16) * sizeof(double)));   // mean | times | running integral, out[2]
         if (s.natoms == 0) continue;
         // the series are stored in the arithmetic type: double, or float in the FP32 mode
         const size_t ser_bytes = (size_t)s.natoms * ctx->DS * ctx->Tld * (precision == TA_PRECISION_FP64 ? sizeof(double) : sizeof(float));
@@ -1233,6 +1239,31 @@ int ta_fetch_by_particle(ta_ctx* ctx, int64_t atom0, int64_t natoms, int layout,
             }
         }
     }
+    return TA_OK;
+}
+
+int ta_green_kubo(ta_ctx* ctx, const double* times, int64_t start, int64_t stop, int64_t step, double initial,
+                  double* integral, double* running, double* slope) {
+    if (!ctx || !ctx->begun || !ctx->have_mean) return fail(ctx, TA_ERR_INVALID, "ta_green_kubo needs the timeseries of a compute call");
+    if (!times) return fail(ctx, TA_ERR_INVALID, "times is null");
+    const int64_t T = ctx->T;
+    if (step < 1 || start < 0 || stop > T || start > stop) return fail(ctx, TA_ERR_INVALID, "bad window");
+    const int64_t n = (stop - start + step - 1) / step;
+    Shard& s = ctx->sh[0];
+    CK(cudaSetDevice(s.dev));
+    double* d_times = s.ts_mean + ctx->Tld;
+    double* d_run = d_times + ctx->Tld;
+    double* d_out = d_run + ctx->Tld;
+    CK(cudaMemcpyAsync(d_times, times, (size_t)T * sizeof(double), cudaMemcpyHostToDevice, s.s_compute));
+    k7_green_kubo<<<1, K7_THREADS, 0, s.s_compute>>>(s.ts_mean, d_times, start, step, (int)n, initial, running ? d_run : nullptr, d_out);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    double out[2] = {0.0, 0.0};
+    CK(cudaMemcpyAsync(out, d_out, sizeof(out), cudaMemcpyDeviceToHost, s.s_compute));
+    if (running && n > 0) CK(cudaMemcpyAsync(running, d_run, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s.s_compute));
+    CK(cudaStreamSynchronize(s.s_compute));
+    if (integral) *integral = out[0];
+    if (slope) *slope = out[1];
     return TA_OK;
 }
 

@@ -20,6 +20,9 @@ Extra keyword arguments (all default to the reference's behaviour):
 ``staging``    ``"auto"`` (default): in-memory readers (MemoryReader) are streamed to the GPU as whole arrays,
                every other reader frame by frame through pinned slabs.  ``"per_frame"``: always frame by frame
                (the path TRR / XTC / NetCDF readers take).
+``postprocess``  ``"host"`` (default): the Green-Kubo helpers are the reference's scipy calls on the host timeseries.
+               ``"device"``: the trapezoid integral and the running integral are computed on the GPU from the
+               timeseries that is still there (kernel K7); Simpson's rule stays on the host.
 ``pin_host``   ``True`` (default): the arrays of an in-memory reader are page-locked on first use so that their
                copies are asynchronous DMA (a one-off cost of ~0.2 s per GB); ``False`` leaves them pageable.
 """
@@ -71,11 +74,14 @@ class VelocityAutocorr(AnalysisBase):
     """
 
     def __init__(self, atomgroup, dim_type="xyz", fft=True, precision="fp64", devices=None,
-                 max_eager_bytes=1 << 26, staging="auto", pin_host=True, **kwargs):
+                 max_eager_bytes=1 << 26, staging="auto", pin_host=True, postprocess="host", **kwargs):
         super().__init__(atomgroup.universe.trajectory, **kwargs)
 
         if isinstance(atomgroup, UpdatingAtomGroup):
             raise TypeError("UpdatingAtomGroups are not valid for VACF computation")
+        if postprocess not in ("host", "device"):
+            raise ValueError("postprocess must be 'host' or 'device'")
+        self._postprocess = postprocess
 
         self.dim_type = dim_type.lower()
         self._dim, self.dim_fac = parse_dim_type(self.dim_type)
@@ -144,6 +150,9 @@ class VelocityAutocorr(AnalysisBase):
         from scipy import integrate
 
         w = self._window(start, stop, step, "computing self-diffusivity")
+        if self._postprocess == "device":
+            lo, hi, st = w.indices(self.n_frames)
+            return self._ctx.green_kubo(self.times, lo, max(lo, hi), st)[0] / self.dim_fac
         return integrate.trapezoid(self.results.timeseries[w], self.times[w]) / self.dim_fac
 
     def self_diffusivity_gk_odd(self, start=0, stop=0, step=1):
@@ -159,7 +168,11 @@ class VelocityAutocorr(AnalysisBase):
         from scipy import integrate
 
         w = self._window(start, stop, step, "plotting")
-        vals = integrate.cumulative_trapezoid(self.results.timeseries[w], self.times[w], initial=initial)
+        if self._postprocess == "device":
+            lo, hi, st = w.indices(self.n_frames)
+            vals = self._ctx.green_kubo(self.times, lo, max(lo, hi), st, initial=initial, running=True)[2]
+        else:
+            vals = integrate.cumulative_trapezoid(self.results.timeseries[w], self.times[w], initial=initial)
         return self.times[w], vals / self.dim_fac
 
     def plot_vacf(self, start=0, stop=0, step=1, xlabel="Time (ps)",

@@ -34,8 +34,8 @@ class ViscosityHelfand(AnalysisBase):
     linear_fit_window : (int, int), optional -- lag window of the linear fit
         whose slope is stored as ``results.viscosity``.
 
-    Extra keyword arguments: ``precision``, ``devices``, ``max_eager_bytes``, ``staging``, ``pin_host``
-    as for :class:`~transport_analysis_b200.velocityautocorr.VelocityAutocorr`, and
+    Extra keyword arguments: ``precision``, ``devices``, ``max_eager_bytes``, ``staging``, ``pin_host``, ``postprocess``
+    (``"device"``: the linear fit of ``linear_fit_window`` is a least-squares slope computed on the GPU) as for :class:`~transport_analysis_b200.velocityautocorr.VelocityAutocorr`, and
 
     ``fft``  ``False`` (default): the direct O(T^2) lag sums of the reference for every lag (viscosity.py:210-226).
              ``True``: the O(T log T) route ``sum (g_i - g_{i+k})^2 = S1[k] - 2 S2[k]`` with ``S2`` from the FFT
@@ -51,7 +51,7 @@ class ViscosityHelfand(AnalysisBase):
 
     def __init__(self, atomgroup, temp_avg=300.0, dim_type="xyz", linear_fit_window=None,
                  precision="fp64", devices=None, max_eager_bytes=1 << 26, fft=False, staging="auto", pin_host=True,
-                 **kwargs):
+                 postprocess="host", **kwargs):
         super().__init__(atomgroup.universe.trajectory, **kwargs)
 
         if isinstance(atomgroup, UpdatingAtomGroup):
@@ -72,7 +72,9 @@ class ViscosityHelfand(AnalysisBase):
         self._fft_auto = fft == "auto"
         if staging not in ("auto", "per_frame"):
             raise ValueError("staging must be 'auto' or 'per_frame'")
-        self._staging, self._pin_host = staging, bool(pin_host)
+        if postprocess not in ("host", "device"):
+            raise ValueError("postprocess must be 'host' or 'device'")
+        self._staging, self._pin_host, self._postprocess = staging, bool(pin_host), postprocess
         self._devices = resolve_devices(devices)
         self._max_eager_bytes = int(max_eager_bytes)
 
@@ -138,7 +140,13 @@ class ViscosityHelfand(AnalysisBase):
             lagtimes = np.arange(1, self.n_frames)
             a, b = self.linear_fit_window[0], self.linear_fit_window[1]
             # x starts at lag 1, y at lag 0: kept exactly as the reference (:240-244)
-            self.results.viscosity = np.polyfit(lagtimes[a:b], self.results.timeseries[a:b], 1)[0]
+            if self._postprocess == "device":
+                # least-squares slope on the GPU (kernel K7) over the same points: x = a + 1 .. , y = timeseries[a:b]
+                lo, hi, _ = slice(a, b).indices(self.n_frames - 1)           # lagtimes has n_frames - 1 entries
+                lag_x = np.arange(1, self.n_frames + 1, dtype=np.float64)
+                self.results.viscosity = self._ctx.green_kubo(lag_x, lo, max(lo, hi), 1)[1]
+            else:
+                self.results.viscosity = np.polyfit(lagtimes[a:b], self.results.timeseries[a:b], 1)[0]
 
     @property
     def running_viscosity(self):
