@@ -5,6 +5,7 @@
 // (sync / shfl_xor16) run unmodified under g++.
 #pragma once
 #include <ucontext.h>
+#include <cstdio>
 #include <cstdlib>
 #include <functional>
 #include <cstring>
@@ -143,14 +144,30 @@ struct EmuCtx {
     static void compiler_fence() {}
     // mbarrier with one arrival per phase: *bar counts completed phases; a wait on parity P returns once the
     // phase of that parity is over (the hardware's try_wait.parity); the bulk load completes when it is issued
-    static void mbar_init(unsigned long long* bar) { *bar = 0; }
+    // bits 0-31: completed phases, 32-47: arrivals of the phase in progress, 48-63: arrivals a phase needs
+    static void mbar_init(unsigned long long* bar, unsigned count = 1u) { *bar = (unsigned long long)count << 48; }
+    static void mbar_arrive(unsigned long long* bar) {
+        const unsigned long long need = *bar >> 48, got = ((*bar >> 32) & 0xffffull) + 1;
+        if (got == need) *bar = (need << 48) | ((*bar + 1) & 0xffffffffull);
+        else *bar = (need << 48) | (got << 32) | (*bar & 0xffffffffull);
+    }
     static void mbar_wait(unsigned long long* bar, unsigned parity) {
-        while ((*bar & 1ull) == (unsigned long long)parity) emu::yield_now();
+        long spins = 0;
+        while ((*bar & 1ull) == (unsigned long long)parity) {
+            if (++spins > 2000000) {     // every other fiber has had two million turns: a deadlock of the kernel body
+                fprintf(stderr, "emu: fiber %d waits forever on mbarrier %p (state %llx) for parity %u\n", active()->current,
+                        (void*)bar, *bar, parity);
+                abort();
+            }
+            emu::yield_now();
+        }
     }
     static void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
         memcpy(dst, src, bytes);
-        ++*bar;
+        mbar_arrive(bar);
     }
+    static unsigned atomic_inc_acq_rel(unsigned* p) { return (*p)++; }
+    static void delay(unsigned clocks) { for (unsigned i = 0; i < clocks / 64; ++i) emu::yield_now(); }
     template <class V> static V ld_stream(const V* p) { return *p; }
 };
 
