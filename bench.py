@@ -736,7 +736,7 @@ def run_b200(args, rank, world, local_rank):
             "cpu_baseline": headline.get("cpu_baseline"), "clocks": headline["clocks"], "parity_check": headline["parity_check"],
             "fft_plan": headline.get("fft_plan"), "setup_s": setup_s,
             "h2d_probe": {"per_rank_gbs": h2d_gbs, "aggregate_gbs": float(sum(h2d_gbs)),
-                          "what": "one contiguous 1 GiB cudaMemcpyAsync from pinned memory per rank, all ranks at once (ta_probe_h2d)",
+                          "what": "twelve back-to-back contiguous 1 GiB cudaMemcpyAsync from pinned memory per rank, all ranks at once (ta_probe_h2d): the sustained concurrent H2D rate of the host",
                           "e2e_h2d_fraction_of_probe": headline["e2e"]["h2d_gbs_per_gpu"] / float(np.mean(h2d_gbs))},
             "fp64_probe_tflops": env.fp64_peak,
         }

@@ -138,9 +138,9 @@ int ta_timer_end(ta_ctx* ctx, float* ms);
 int ta_last_kernel_ms(ta_ctx* ctx, float* ms);
 /* Probes for the roofline denominators bench.py reports beside MEASURED_PEAKS.json (which holds HBM and bf16 only):
  * ta_probe_fp64: FP64 FMA rate of the context's first device, TFLOP/s (independent DFMA chains on every SM, CUDA
- * events on the compute stream).  ta_probe_h2d: rate of one contiguous `bytes`-long cudaMemcpyAsync from pinned host
- * memory to the context's first device, GB/s (the ceiling the staging copies of ta_stage_bulk are measured against;
- * call it on all ranks at once to see the box's concurrent ceiling). */
+ * events on the compute stream).  ta_probe_h2d: sustained rate of twelve back-to-back contiguous `bytes`-long
+ * cudaMemcpyAsync from pinned host memory to the context's first device, GB/s (the ceiling the staging copies of
+ * ta_stage_bulk are measured against; call it on all ranks at once to see the box's concurrent ceiling). */
 int ta_probe_fp64(ta_ctx* ctx, double* tflops);
 int ta_probe_h2d(ta_ctx* ctx, uint64_t bytes, double* gbps);
 /* Overwrite a 512 MB scratch buffer so that nothing of the inputs stays in L2

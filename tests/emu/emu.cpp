@@ -11,7 +11,6 @@
 #include "../../transport_analysis_b200/csrc/fft_core.cuh"
 #include "../../transport_analysis_b200/csrc/windowed_core.cuh"
 #include "../../transport_analysis_b200/csrc/k1_fast.cuh"
-#include "../../transport_analysis_b200/csrc/k1_pipe.cuh"
 #include "fiber_cta.h"
 
 using namespace ta;
@@ -20,10 +19,10 @@ using namespace ta;
 template <typename R>
 static std::vector<R> series_as(const double* series, size_t n) { return std::vector<R>(series, series + n); }
 
-template <typename R, typename ST = R>
+template <typename R>
 static int run_fft(const double* series_f64, int T, int D, int Tld, int nthr, double* row, double* partial) {
-    const std::vector<ST> series_r = series_as<ST>(series_f64, (size_t)D * Tld);
-    const ST* series = series_r.data();
+    const std::vector<R> series_r = series_as<R>(series_f64, (size_t)D * Tld);
+    const R* series = series_r.data();
     FftPlanHost hp;
     int rc = ta_build_fft_plan(T, &hp);
     if (rc) return rc;
@@ -44,7 +43,7 @@ static int run_fft(const double* series_f64, int T, int D, int Tld, int nthr, do
     for (int r = 0; r < 2; ++r) {
         PHASE(fft_zero_acc<R>(tid, nthr, sd.data(), t));
         for (int d = 0; d < D; ++d) {
-            PHASE((fft_load<R, ST>(tid, nthr, buf.data(), series + (size_t)d * Tld, t, r)));
+            PHASE(fft_load<R>(tid, nthr, buf.data(), series + (size_t)d * Tld, t, r));
             int size = t.H;
             for (int ps = 0; ps < t.npasses; ++ps) {
                 int s = size / t.radix[ps];
@@ -64,10 +63,10 @@ static int run_fft(const double* series_f64, int T, int D, int Tld, int nthr, do
     return 0;
 }
 
-template <typename R, typename ST = R>
+template <typename R>
 static int run_win(const double* series_f64, int T, int D, int Tld, int mode, int nwarps, int nsplit, double* res) {
-    const std::vector<ST> series_r = series_as<ST>(series_f64, (size_t)D * Tld);
-    const ST* series = series_r.data();
+    const std::vector<R> series_r = series_as<R>(series_f64, (size_t)D * Tld);
+    const R* series = series_r.data();
     // the kernel body itself (windowed_core.cuh win_body) for one particle, CTAs of nwarps warps, one per part of the
     // particle (nsplit); returns the un-normalised lag sums (row * (T - k) [* D * denom])
     const int ne = win_smem_elems(T);
@@ -81,8 +80,8 @@ static int run_win(const double* series_f64, int T, int D, int Tld, int mode, in
     a.scratch = nullptr; a.scratch_stride = 0; a.nsplit = nsplit;
     const int nthr = 32 * nwarps;
     for (int bid = 0; bid < nblk; ++bid) {
-        if (mode == TA_WIN_PRODUCT) emu::run_cta(nthr, [&](int tid) { win_body<R, TA_WIN_PRODUCT, emu::EmuCtx, false, ST>(a, sm, tid, nthr, bid, nblk); });
-        else emu::run_cta(nthr, [&](int tid) { win_body<R, TA_WIN_SQDIFF, emu::EmuCtx, false, ST>(a, sm, tid, nthr, bid, nblk); });
+        if (mode == TA_WIN_PRODUCT) emu::run_cta(nthr, [&](int tid) { win_body<R, TA_WIN_PRODUCT, emu::EmuCtx>(a, sm, tid, nthr, bid, nblk); });
+        else emu::run_cta(nthr, [&](int tid) { win_body<R, TA_WIN_SQDIFF, emu::EmuCtx>(a, sm, tid, nthr, bid, nblk); });
     }
     for (int k = 0; k < T; ++k) {
         double psum = 0.0;                              // every lag is finished by exactly one CTA
@@ -94,16 +93,16 @@ static int run_win(const double* series_f64, int T, int D, int Tld, int mode, in
     return 0;
 }
 
-template <int R1, typename RT, typename ST = RT>
+template <int R1, typename RT>
 static int run_k1fast(const double* series_f64, int T, int D, int Tld, int natoms, int nblk, double* by_particle,
                       double* partial) {
     K1FastPlan p;
     int rc = k1f_build_plan(T, Tld, R1, &p);
     if (rc) return rc;
-    const std::vector<ST> series = series_as<ST>(series_f64, (size_t)natoms * D * Tld);
+    const std::vector<RT> series = series_as<RT>(series_f64, (size_t)natoms * D * Tld);
     const std::vector<RT> omega(p.omega.begin(), p.omega.end()), tw2(p.tw2.begin(), p.tw2.end()),
         wbase(p.wbase.begin(), p.wbase.end()), inv(p.inv.begin(), p.inv.end());
-    K1FArgs<RT, ST> a;
+    K1FArgs<RT> a;
     a.series = series.data(); a.by_particle = by_particle; a.partial = partial;
     a.omega = reinterpret_cast<const cplx<RT>*>(omega.data());
     a.tw2 = reinterpret_cast<const cplx<RT>*>(tw2.data());
@@ -112,74 +111,41 @@ static int run_k1fast(const double* series_f64, int T, int D, int Tld, int natom
     a.inv = inv.data();
     a.natoms = natoms; a.D = D; a.DS = D; a.T = T; a.nh = p.nh; a.Tld = Tld;
     constexpr bool PREF = k1f_prefetch(R1, (int)sizeof(RT));        // the build the library ships for this (R1, RT)
-    std::vector<unsigned char> smem(k1f_smem_bytes(R1, PREF, (int)sizeof(RT), (int)sizeof(ST)) + 64);
+    std::vector<unsigned char> smem(k1f_smem_bytes(R1, PREF, (int)sizeof(RT)) + 64);
     unsigned char* sm = smem.data() + (16 - ((uintptr_t)smem.data() & 15)) % 16;
     for (int bid = 0; bid < nblk; ++bid)
-        emu::run_cta(k1f_threads(R1), [&](int tid) { k1f_body<R1, k1f_threads(R1), emu::EmuCtx, RT, PREF, ST>(a, sm, tid, bid, nblk); });
+        emu::run_cta(k1f_threads(R1), [&](int tid) { k1f_body<R1, k1f_threads(R1), emu::EmuCtx, RT, PREF>(a, sm, tid, bid, nblk); });
     return 0;
 }
 
-// the pipelined body (k1_pipe.cuh): FP64 arithmetic on float series, two FFT buffers, mbarriers
-template <int R1, bool PREF>
-static int run_k1pipe(const double* series_f64, int T, int D, int Tld, int natoms, int nblk, double* by_particle, double* partial) {
-    K1FastPlan p;
-    int rc = k1f_build_plan(T, Tld, R1, &p);
-    if (rc) return rc;
-    const std::vector<float> series = series_as<float>(series_f64, (size_t)natoms * D * Tld);
-    K1FArgs<double, float> a;
-    a.series = series.data(); a.by_particle = by_particle; a.partial = partial;
-    a.omega = reinterpret_cast<const cplx<double>*>(p.omega.data());
-    a.tw2 = reinterpret_cast<const cplx<double>*>(p.tw2.data());
-    a.map = p.map.data();
-    a.wbase = reinterpret_cast<const cplx<double>*>(p.wbase.data());
-    a.inv = p.inv.data();
-    a.natoms = natoms; a.D = D; a.DS = D; a.T = T; a.nh = p.nh; a.Tld = Tld;
-    std::vector<unsigned char> smem(k1p_smem_bytes(R1, 8, 4, PREF) + 64);
-    unsigned char* sm = smem.data() + (16 - ((uintptr_t)smem.data() & 15)) % 16;
-    for (int bid = 0; bid < nblk; ++bid)
-        emu::run_cta(k1f_threads(R1), [&](int tid) { k1p_body<R1, k1f_threads(R1), emu::EmuCtx, double, float, PREF>(a, sm, tid, bid, nblk); });
-    return 0;
-}
-
-template <typename RT, typename ST = RT>
+template <typename RT>
 static int run_k1fast_any(const double* series, int T, int D, int Tld, int natoms, int nblk, int R1, double* by_particle, double* partial) {
     switch (R1) {
-        case 4: return run_k1fast<4, RT, ST>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-        case 6: return run_k1fast<6, RT, ST>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-        case 8: return run_k1fast<8, RT, ST>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-        case 10: return run_k1fast<10, RT, ST>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-        case 12: return run_k1fast<12, RT, ST>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-        case 16: return run_k1fast<16, RT, ST>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-        case 20: return run_k1fast<20, RT, ST>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-        case 24: return run_k1fast<24, RT, ST>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 4: return run_k1fast<4, RT>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 6: return run_k1fast<6, RT>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 8: return run_k1fast<8, RT>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 10: return run_k1fast<10, RT>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 12: return run_k1fast<12, RT>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 16: return run_k1fast<16, RT>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 20: return run_k1fast<20, RT>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        case 24: return run_k1fast<24, RT>(series, T, D, Tld, natoms, nblk, by_particle, partial);
     }
     return -1;
 }
 
 extern "C" {
 int emu_k1fast_r1(int T) { return k1f_choose_r1(T); }
-// the three-pass kernel body as shipped for (R1, precision): use_f32 = 0 FP64, 1 FP32 (float series, float arithmetic),
-// 2 FP64 arithmetic on float series (float sources: the upcast happens where the kernel loads the series)
+// the three-pass kernel body as shipped for (R1, precision): use_f32 = 0 FP64, 1 FP32 (float series, float arithmetic)
 int emu_k1fast(const double* series, int T, int D, int Tld, int natoms, int nblk, int R1, int use_f32, double* by_particle,
                double* partial) {
-    if (use_f32 == 2) return run_k1fast_any<double, float>(series, T, D, Tld, natoms, nblk, R1, by_particle, partial);
     return use_f32 ? run_k1fast_any<float>(series, T, D, Tld, natoms, nblk, R1, by_particle, partial)
                    : run_k1fast_any<double>(series, T, D, Tld, natoms, nblk, R1, by_particle, partial);
 }
-int emu_k1pipe(const double* series, int T, int D, int Tld, int natoms, int nblk, int R1, int pref, double* by_particle, double* partial) {
-    if (R1 == 16) return pref ? run_k1pipe<16, true>(series, T, D, Tld, natoms, nblk, by_particle, partial)
-                              : run_k1pipe<16, false>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-    if (R1 == 20) return pref ? run_k1pipe<20, true>(series, T, D, Tld, natoms, nblk, by_particle, partial)
-                              : run_k1pipe<20, false>(series, T, D, Tld, natoms, nblk, by_particle, partial);
-    return -1;
-}
 int emu_fft_acf(const double* series, int T, int D, int Tld, int nthr, int use_f32, double* row, double* partial) {
-    if (use_f32 == 2) return run_fft<double, float>(series, T, D, Tld, nthr, row, partial);
     return use_f32 ? run_fft<float>(series, T, D, Tld, nthr, row, partial)
                    : run_fft<double>(series, T, D, Tld, nthr, row, partial);
 }
 int emu_windowed(const double* series, int T, int D, int Tld, int mode, int nwarps, int nsplit, int use_f32, double* res) {
-    if (use_f32 == 2) return run_win<double, float>(series, T, D, Tld, mode, nwarps, nsplit, res);
     return use_f32 ? run_win<float>(series, T, D, Tld, mode, nwarps, nsplit, res)
                    : run_win<double>(series, T, D, Tld, mode, nwarps, nsplit, res);
 }

@@ -173,49 +173,3 @@ def test_three_pass_kernel_at_the_ends_of_every_length_range(emu, T, R1):
     bp, part = emu_fast(emu, x, 1, R1)
     assert_close_normwise(bp[0], oracle.tidynamics_acf(x[:, 0, :]), 1e-12, f"T={T} R1={R1}")
     np.testing.assert_array_equal(part[0], bp[0])
-
-
-def test_float_series_under_fp64_arithmetic_give_the_same_bits(emu):
-    """Float sources are stored as float in HBM and upcast where the kernels load them (f32=2): bit-identical to the
-    double storage, for the three-pass kernel, the general kernel and the windowed kernel."""
-    rng = np.random.default_rng(11)
-    for T, D, N, nblk in [(1600, 3, 1, 1), (4999, 2, 2, 1), (10000, 3, 2, 2), (11000, 1, 1, 1)]:
-        x = rng.standard_normal((T, N, D)).astype(np.float32).astype(np.float64)
-        wide = emu_fast(emu, x, nblk)
-        narrow = emu_fast(emu, x, nblk, f32=2)
-        assert np.array_equal(wide[0], narrow[0]) and np.array_equal(wide[1], narrow[1])
-    x = rng.standard_normal((777, 3)).astype(np.float32).astype(np.float64)
-    assert np.array_equal(emu_fft(emu, x), emu_fft(emu, x, f32=2))
-    for mode in (0, 1):
-        assert np.array_equal(emu_win(emu, x, mode), emu_win(emu, x, mode, f32=2))
-
-
-# ------------------------------------------------------------------ pipelined K1 (k1_pipe.cuh) under the fiber emulator
-def emu_pipe(lib, x, nblk=1, R1=None, pref=1):
-    """x: [T, N, D], float-representable.  Runs k1p_body for nblk CTAs of 16*R1 fibers."""
-    T, N, D = x.shape
-    R1 = R1 or lib.emu_k1fast_r1(T)
-    Tld = (T + 15) // 16 * 16
-    ser = np.zeros((N, D, Tld))
-    ser[:, :, :T] = x.transpose(1, 2, 0)
-    bp, part = np.zeros((N, Tld)), np.zeros((nblk, Tld))
-    assert lib.emu_k1pipe(_p(ser), T, D, Tld, N, nblk, R1, pref, _p(bp), _p(part)) == 0
-    assert np.all(bp[:, T:] == 0)
-    return bp[:, :T], part[:, :T]
-
-
-@pytest.mark.parametrize("T,D,N,nblk", [(10000, 3, 1, 1), (10000, 3, 5, 2), (9999, 2, 3, 1), (8192, 1, 4, 2), (7000, 3, 2, 3),
-                                        (8000, 2, 3, 1), (10240, 1, 1, 1), (6200, 3, 2, 1)])
-def test_pipelined_kernel_body_gives_the_bits_of_the_barrier_kernel(emu, T, D, N, nblk):
-    """Same butterflies, same tables, same order of every floating-point operation: the pipelined body (two buffers,
-    mbarriers, chains interleaved front / back) must reproduce the barrier body bit for bit, for every D (the chain
-    stream differs), several particles per CTA (the stream crosses particles) and CTAs without work (nblk > N)."""
-    x = np.random.default_rng(T + D + N).standard_normal((T, N, D)).astype(np.float32).astype(np.float64)
-    R1 = emu.emu_k1fast_r1(T)
-    assert R1 in (16, 20)
-    ref_bp, ref_part = emu_fast(emu, x, nblk, R1, f32=2)
-    for pref in (1, 0):          # series through the bulk-copy prefetch buffer / straight from global memory
-        bp, part = emu_pipe(emu, x, nblk, R1, pref)
-        assert np.array_equal(bp, ref_bp)
-        assert np.array_equal(part, ref_part)
-    assert_close_normwise(bp[0], oracle.tidynamics_acf(x[:, 0, :]), 1e-12, f"T={T}")

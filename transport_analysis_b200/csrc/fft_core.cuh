@@ -199,15 +199,14 @@ TA_HD void dit_pass_any(int radix, int tid, int nthr, cplx<R>* buf, const FftTab
 // the next even index) as z[n] = x[2n] + i x[2n+1], n < H, twisted by
 // w_{2H}^{n} = w_L^{2n} for the odd residue.
 // ---------------------------------------------------------------------------
-template <typename R, typename ST = R>
-TA_HD void fft_load(int tid, int nthr, cplx<R>* buf, const ST* series, const FftTables<R>& t, int r) {
+template <typename R>
+TA_HD void fft_load(int tid, int nthr, cplx<R>* buf, const R* series, const FftTables<R>& t, int r) {
     const int nh = (t.T + 1) / 2;
-    const cplx<ST>* src = reinterpret_cast<const cplx<ST>*>(series);
+    const cplx<R>* src = reinterpret_cast<const cplx<R>*>(series);
     for (int n = tid; n < t.H; n += nthr) {
         cplx<R> z = cmake<R>((R)0, (R)0);
         if (n < nh) {
-            const cplx<ST> zs = src[n];
-            z = cmake<R>((R)zs.x, (R)zs.y);
+            z = src[n];
             if (r) z = cmul(z, tw_get(t, 2 * n));
         }
         buf[n] = z;

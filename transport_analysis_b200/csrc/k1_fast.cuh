@@ -48,11 +48,9 @@
 
 namespace ta {
 
-template <typename RT, typename ST = RT>
+template <typename RT>
 struct K1FArgs {
-    const ST* series;            // [natoms][DS][Tld], stored as ST (the arithmetic type RT, or float under FP64 arithmetic when the source was
-                                 // float: the exact upcast then happens in P1).  The first D rows of a particle are transformed (DS > D:
-                                 // Helfand keeps a row of sum_d g^2 behind them)
+    const RT* series;            // [natoms][DS][Tld]: the first D rows of a particle are transformed (DS > D: Helfand keeps a row of sum_d g^2 behind them)
     double* by_particle;         // [natoms][Tld]
     double* partial;             // [grid][Tld]
     const cplx<RT>* omega;       // [256]      w_{2H}^j
@@ -62,16 +60,14 @@ struct K1FArgs {
     const RT* inv;               // [Tld]      1 / (L (T - k)), 0 beyond T
     int natoms, D, DS, T, nh;
     long long Tld;
-    int stagger = 0;             // pipelined build: start-up delay (clocks) of warps 4-7
-    long long* trace = nullptr;  // -DTA_EXPERIMENTS builds: stage time stamps of CTA 0 ([warp][96 chains][8 events])
 };
 
 constexpr uint32_t K1F_SELF0 = 1u << 30;   // butterfly holding g = 0 (pairs k <-> 16-k in-thread)
 constexpr uint32_t K1F_SELF8 = 1u << 31;   // butterfly holding g = H/2 (pairs k <-> 15-k in-thread)
 
 // dynamic shared memory: FFT buffer (padded) + omega + tw2 (+ series buffer and its mbarrier), in complex elements of RT
-constexpr int k1f_smem_bytes(int R1, bool pref, int real_bytes, int store_bytes = 0) {
-    return (256 * R1 + 16 * R1 + 256 + 240) * 2 * real_bytes + (pref ? 256 * R1 * 2 * (store_bytes ? store_bytes : real_bytes) + 32 : 0);
+constexpr int k1f_smem_bytes(int R1, bool pref, int real_bytes) {
+    return (256 * R1 + 16 * R1 + 256 + 240 + (pref ? 256 * R1 + 2 : 0)) * 2 * real_bytes;
 }
 // Threads per CTA (NT): one radix-16 butterfly of P2 / P3 per thread (a pass has NV = 16 R1 of them; whole warps,
 // so the lane exchange of P3 stays inside a warp).  Measured on B200 at R1 = 20, 100k x 10k
@@ -114,10 +110,9 @@ TA_HD void k1f_p1_twiddles(C om, int r, C* e, C* g) {
 // device these are the hardware's, in tests/emu they are cooperative-fiber versions so the very same code runs on
 // the CPU.
 // ---------------------------------------------------------------------------
-template <int R1, int NT, class Ctx, typename RT, bool PREF, typename ST = RT>
-TA_HD void k1f_body(const K1FArgs<RT, ST>& A, unsigned char* smem_raw, int tid, int bid, int nblk) {
+template <int R1, int NT, class Ctx, typename RT, bool PREF>
+TA_HD void k1f_body(const K1FArgs<RT>& A, unsigned char* smem_raw, int tid, int bid, int nblk) {
     using C = cplx<RT>;
-    using CS = cplx<ST>;
     constexpr int H = 256 * R1;
     constexpr int NV = 16 * R1;          // radix-16 butterflies per pass ("virtual threads")
     constexpr int NB = (NV + NT - 1) / NT;   // butterfly rounds of P2 / P3; a thread owns vt = tid + it NT < NV
@@ -126,7 +121,7 @@ TA_HD void k1f_body(const K1FArgs<RT, ST>& A, unsigned char* smem_raw, int tid, 
     C* buf = reinterpret_cast<C*>(smem_raw);         // H + H/16 elements, padded layout
     C* s_om = buf + (H + H / 16);                    // 256
     C* s_tw2 = s_om + 256;                           // 240
-    CS* pre = reinterpret_cast<CS*>(s_tw2 + 240);    // PREF: H elements, the series of the coming chain as it lies in HBM
+    C* pre = s_tw2 + 240;                            // PREF: H elements, the series of the coming chain as it lies in HBM
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(pre + H);   // PREF: "series has landed" (16-byte slot)
     unsigned pre_phase = 0;
     const C czero = cmake<RT>((RT)0, (RT)0);
@@ -139,14 +134,14 @@ TA_HD void k1f_body(const K1FArgs<RT, ST>& A, unsigned char* smem_raw, int tid, 
     const int nh = A.nh;
     // bytes of one series the bulk copy moves: nh complex values, rounded up to the 16 bytes the engine works in
     // (FP32: the extra 8 bytes are the zero padding of the row, Tld is a multiple of 16 elements)
-    const unsigned ser_bytes = ((unsigned)nh * (unsigned)sizeof(CS) + 15u) & ~15u;
+    const unsigned ser_bytes = ((unsigned)nh * (unsigned)sizeof(C) + 15u) & ~15u;
     if (PREF && tid == 0 && bid < A.natoms) Ctx::bulk_load(pre, A.series + (size_t)bid * A.DS * A.Tld, ser_bytes, mbar);
     const int j2 = tid & 15;                         // NT is a multiple of 16: the same for every owned butterfly
     cd* part = reinterpret_cast<cd*>(A.partial + (size_t)bid * A.Tld);
     const C* inv2 = reinterpret_cast<const C*>(A.inv);
 
     for (int atom = bid; atom < A.natoms; atom += nblk) {
-        const ST* ser = A.series + (size_t)atom * A.DS * A.Tld;
+        const RT* ser = A.series + (size_t)atom * A.DS * A.Tld;
         cd* row = reinterpret_cast<cd*>(A.by_particle + (size_t)atom * A.Tld);
         for (int r = 0; r < 2; ++r) {
             RT acc_s[NB][8], acc_d[NB][8], acc8[NB];
@@ -159,7 +154,7 @@ TA_HD void k1f_body(const K1FArgs<RT, ST>& A, unsigned char* smem_raw, int tid, 
 
             for (int d = 0; d < A.D; ++d) {
                 // ---------------- P1: series -> registers -> shared
-                const CS* src = reinterpret_cast<const CS*>(ser + (size_t)d * A.Tld);
+                const C* src = reinterpret_cast<const C*>(ser + (size_t)d * A.Tld);
                 for (int j = tid; j < 256; j += NT) {
                     C x[R1];
                     if (PREF) {
@@ -167,15 +162,13 @@ TA_HD void k1f_body(const K1FArgs<RT, ST>& A, unsigned char* smem_raw, int tid, 
 #pragma unroll
                         for (int q = 0; q < R1; ++q) {
                             const int n = j + 256 * q;
-                            if (n < nh) { const CS zs = pre[n]; x[q] = cmake<RT>((RT)zs.x, (RT)zs.y); }
-                            else x[q] = czero;
+                            x[q] = (n < nh) ? pre[n] : czero;
                         }
                     } else {
 #pragma unroll
                         for (int q = 0; q < R1; ++q) {
                             const int n = j + 256 * q;
-                            if (n < nh) { const CS zs = Ctx::ld_stream(src + n); x[q] = cmake<RT>((RT)zs.x, (RT)zs.y); }
-                            else x[q] = czero;
+                            x[q] = (n < nh) ? Ctx::ld_stream(src + n) : czero;
                         }
                     }
                     if (r) {
@@ -203,7 +196,7 @@ TA_HD void k1f_body(const K1FArgs<RT, ST>& A, unsigned char* smem_raw, int tid, 
                     // every P1 thread has read the prefetch buffer: hand it to the bulk-copy engine for the next chain
                     pre_phase ^= 1u;
                     if (tid == NT - 1) {
-                        const ST* nxt = nullptr;
+                        const RT* nxt = nullptr;
                         if (d + 1 < A.D) nxt = ser + (size_t)(d + 1) * A.Tld;
                         else if (r == 0) nxt = ser;
                         else if (atom + nblk < A.natoms) nxt = ser + (size_t)nblk * A.DS * A.Tld;

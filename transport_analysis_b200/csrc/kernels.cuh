@@ -9,7 +9,6 @@
 #include "fft_core.cuh"
 #include "windowed_core.cuh"
 #include "k1_fast.cuh"
-#include "k1_pipe.cuh"
 
 namespace ta {
 
@@ -75,12 +74,11 @@ k0_stage(const SRC* __restrict__ v, const SRC* __restrict__ x, const double* __r
 // ---------------------------------------------------------------------------
 // K1: FFT autocorrelation, one particle per CTA iteration.
 // ---------------------------------------------------------------------------
-template <typename R, typename ST = R>
+template <typename R>
 struct K1Args {
     FftTables<R> t;              // tw_lo / tw_hi point to GLOBAL copies here
     int nlo, nhi;
-    const ST* series;            // [natoms][DS][Tld]  (stored as ST: the arithmetic type, or float under FP64 arithmetic
-                                 // when the source was float; the first D rows are transformed)
+    const R* series;             // [natoms][DS][Tld]  (stored in the arithmetic type; the first D rows are transformed)
     double* by_particle;         // [natoms][Tld]
     double* partial;             // [gridDim.x][Tld]
     int natoms, D, DS;
@@ -94,9 +92,9 @@ constexpr int K1_MAX_THREADS = 640;
 // SCRATCH = false: the H-point buffer and the pair accumulators live in shared memory (H up to ~9,600 in FP64).
 // SCRATCH = true : they live in a per-CTA global work area (served by L2), the twiddle tables stay in shared memory:
 //                  the same passes, slower, for any T -- the FFT route never has to refuse a trajectory for its length.
-template <typename R, bool SCRATCH = false, typename ST = R>
+template <typename R, bool SCRATCH = false>
 __global__ void __launch_bounds__(K1_MAX_THREADS)
-k1_fft_acf(const K1Args<R, ST> args) {
+k1_fft_acf(const K1Args<R> args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int H = args.t.H;
     unsigned char* work = SCRATCH ? args.scratch + (size_t)blockIdx.x * (size_t)args.scratch_stride : smem_raw;
@@ -115,12 +113,12 @@ k1_fft_acf(const K1Args<R, ST> args) {
 
     double* partial = args.partial + (size_t)blockIdx.x * args.Tld;
     for (int a = blockIdx.x; a < args.natoms; a += gridDim.x) {
-        const ST* ser = args.series + (size_t)a * args.DS * args.Tld;
+        const R* ser = args.series + (size_t)a * args.DS * args.Tld;
         double* row = args.by_particle + (size_t)a * args.Tld;
         for (int r = 0; r < 2; ++r) {
             fft_zero_acc<R>(tid, nthr, sd, t);
             for (int d = 0; d < args.D; ++d) {
-                fft_load<R, ST>(tid, nthr, buf, ser + (size_t)d * args.Tld, t, r);
+                fft_load<R>(tid, nthr, buf, ser + (size_t)d * args.Tld, t, r);
                 __syncthreads();
                 int size = H;
                 for (int ps = 0; ps < t.npasses; ++ps) {
@@ -198,36 +196,11 @@ struct DevCtx {
 #endif
     }
     // mbarrier with one arrival per phase (the thread that issues the bulk load)
-    static TA_HD void mbar_init(unsigned long long* bar, unsigned count = 1u) {
+    static TA_HD void mbar_init(unsigned long long* bar) {
 #if defined(__CUDA_ARCH__)
         const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#endif
-    }
-    // one arrival (release at CTA scope: the caller's -- and, after a __syncwarp, its warp's -- earlier shared-memory
-    // accesses are ordered before it)
-    static TA_HD void mbar_arrive(unsigned long long* bar) {
-#if defined(__CUDA_ARCH__)
-        const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
-#endif
-    }
-    static TA_HD void delay(unsigned clocks) {
-#if defined(__CUDA_ARCH__)
-        const long long t0 = clock64();
-        while (clock64() - t0 < (long long)clocks) { }
-#endif
-    }
-    // shared-memory counter: returns the old value
-    static TA_HD unsigned atomic_inc_acq_rel(unsigned* p) {
-#if defined(__CUDA_ARCH__)
-        const unsigned a = (unsigned)__cvta_generic_to_shared(p);
-        unsigned old;
-        asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(a) : "memory");
-        return old;
-#else
-        return (*p)++;
 #endif
     }
     // dst[0..bytes) (shared) <- src (global) by the bulk-copy engine (TMA); completion flips the phase of `bar`
@@ -253,12 +226,12 @@ struct DevCtx {
 };
 
 // One kernel per (R1, arithmetic type).  NT = 16 R1 threads; the bulk series prefetch where k1f_prefetch says so.
-template <int R1, typename RT, typename ST = RT>
+template <int R1, typename RT>
 __global__ void __launch_bounds__(k1f_threads(R1), k1f_min_blocks(k1f_threads(R1), (int)sizeof(RT)))
-k1f_fft_acf(const K1FArgs<RT, ST> args) {
+k1f_fft_acf(const K1FArgs<RT> args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    k1f_body<R1, k1f_threads(R1), DevCtx, RT, k1f_prefetch(R1, (int)sizeof(RT)), ST>(args, smem_raw, (int)threadIdx.x, (int)blockIdx.x,
-                                                                                     (int)gridDim.x);
+    k1f_body<R1, k1f_threads(R1), DevCtx, RT, k1f_prefetch(R1, (int)sizeof(RT))>(args, smem_raw, (int)threadIdx.x, (int)blockIdx.x,
+                                                                                 (int)gridDim.x);
 }
 
 // The FP64 kernel of ten warps (R1 = 20) with the register cap stated outright instead of derived from launch bounds.
@@ -267,22 +240,12 @@ k1f_fft_acf(const K1FArgs<RT, ST> args) {
 // 16-32 B of spills, __maxnreg__(184) 166 registers and none -- 24.2 -> 23.5 ms at 100k x 10k (caps 152 / 160 / 168 /
 // 176 / 184: 24.21 / 24.08 / 23.66 / 23.52 / 23.46 ms; 200 does not fit).
 constexpr int K1F_MAXREG = 184;
-template <int R1, typename RT, typename ST = RT>
+template <int R1, typename RT>
 __global__ void __maxnreg__(K1F_MAXREG)
-k1f_fft_acf_mr(const K1FArgs<RT, ST> args) {
+k1f_fft_acf_mr(const K1FArgs<RT> args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    k1f_body<R1, k1f_threads(R1), DevCtx, RT, k1f_prefetch(R1, (int)sizeof(RT)), ST>(args, smem_raw, (int)threadIdx.x, (int)blockIdx.x,
-                                                                                     (int)gridDim.x);
-}
-
-// The pipelined build of the same transform (k1_pipe.cuh): FP64 arithmetic on float series, two FFT buffers, mbarriers
-// instead of CTA barriers.  One CTA of 16 R1 threads per SM.
-// 168 registers: three warps of a sub-partition share 16,384.
-template <int R1, bool PREF>
-__global__ void __maxnreg__(168)
-k1p_fft_acf(const K1FArgs<double, float> args) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    k1p_body<R1, k1f_threads(R1), DevCtx, double, float, PREF>(args, smem_raw, (int)threadIdx.x, (int)blockIdx.x, (int)gridDim.x);
+    k1f_body<R1, k1f_threads(R1), DevCtx, RT, k1f_prefetch(R1, (int)sizeof(RT))>(args, smem_raw, (int)threadIdx.x, (int)blockIdx.x,
+                                                                                 (int)gridDim.x);
 }
 
 // ---------------------------------------------------------------------------
@@ -292,11 +255,11 @@ k1p_fft_acf(const K1FArgs<double, float> args) {
 // ---------------------------------------------------------------------------
 constexpr int KW_MAX_THREADS = 512;
 
-template <typename R, int MODE, bool SCRATCH = false, typename ST = R>
+template <typename R, int MODE, bool SCRATCH = false>
 __global__ void __launch_bounds__(KW_MAX_THREADS)
 k_windowed(const WinArgs args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    win_body<R, MODE, DevCtx, SCRATCH, ST>(args, smem_raw, (int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x);
+    win_body<R, MODE, DevCtx, SCRATCH>(args, smem_raw, (int)threadIdx.x, (int)blockDim.x, (int)blockIdx.x, (int)gridDim.x);
 }
 
 // ---------------------------------------------------------------------------

@@ -141,10 +141,6 @@ struct ta_ctx {
     int D = 0, dims[3] = {0, 1, 2};
     int DS = 0;              // series rows per particle: D, + 1 row of sum_d g^2 for Helfand in FP64 (K5 reads it)
     int src_dtype = TA_DTYPE_F32, n_fields = 1, precision = TA_PRECISION_FP64;
-    // FP64 arithmetic on float series: a float source whose values go into the series unchanged (velocities; not the
-    // Helfand moment, which is a double product) is stored as float and upcast -- exactly, as the reference's f64
-    // arrays do (velocityautocorr.py:145-147, 192-194) -- where the kernels load it: half the HBM footprint and traffic
-    bool narrow = false;
     size_t elt = 4;
     int64_t frames_staged = 0;
     // pinned slab ring
@@ -161,17 +157,13 @@ struct ta_ctx {
     int fast_r1 = 0;         // > 0: the plan is for the three-pass path (k1_fast.cuh) with this R1
     // debugging knobs, read from the environment ONCE when the context is created (never on a launch path):
     //   TA_B200_K1_PATH = general        the general mixed-radix FFT kernel even where the three-pass kernel applies
-    //                   = lockstep       the three-pass kernel with CTA barriers even where the pipelined one applies
-    //                                    (the tests compare the kernels with each other)
-    //   TA_B200_SERIES = wide            float sources stored as double in HBM (tests: same bits as the float storage)
+    //                                    (the tests compare the two kernels with each other)
     //   TA_B200_BULK_CHUNK = n           particles per staging chunk of ta_stage_bulk (tests: any chunking, same bits)
     //   TA_B200_HELFAND_FFT_THR = x      refinement threshold of ta_helfand_fft (scripts/helfand_fft_error_constant.py)
-    bool opt_general_fft = false, opt_lockstep_fft = false, opt_wide_series = false, opt_k1p_pref = false;
-    int opt_k1p_stagger = 0;
+    bool opt_general_fft = false;
     int64_t opt_bulk_chunk = 0;
     double opt_helfand_thr = -2.0;       // < -1.5: the built-in rule
     int k1_threads = 0, k1_smem = 0, k1_grid = 0;
-    bool k1_pipelined = false;
     bool have_mean = false;  // ts_mean of the first shard holds the result of a compute call
     int64_t launches = 0;
     long long helfand_fft_flagged = 0;   // (particle, lag) pairs the last ta_helfand_fft evaluated exactly; -1: all (K3 took over)
@@ -304,7 +296,7 @@ int launch_k0_t(ta_ctx* ctx, Shard& s, const void* vsrc, const void* xsrc, int64
 
 int launch_k0(ta_ctx* ctx, Shard& s, const void* vsrc, const void* xsrc, int64_t a0, int64_t n, int64_t nframes,
               int64_t frame0, cudaStream_t stream) {
-    const bool f32src = ctx->src_dtype == TA_DTYPE_F32, fp64 = ctx->precision == TA_PRECISION_FP64 && !ctx->narrow;
+    const bool f32src = ctx->src_dtype == TA_DTYPE_F32, fp64 = ctx->precision == TA_PRECISION_FP64;
     if (f32src) return fp64 ? launch_k0_t<float, double>(ctx, s, vsrc, xsrc, a0, n, nframes, frame0, stream)
                             : launch_k0_t<float, float>(ctx, s, vsrc, xsrc, a0, n, nframes, frame0, stream);
     return fp64 ? launch_k0_t<double, double>(ctx, s, vsrc, xsrc, a0, n, nframes, frame0, stream)
@@ -497,7 +489,7 @@ int ensure_fft_plan(ta_ctx* ctx) {
     return TA_OK;
 }
 
-template <typename R, typename ST = R>
+template <typename R>
 int launch_fft(ta_ctx* ctx, std::vector<int>* grids) {
     const FftPlanHost& p = ctx->plan;
     const int nlo = 1 << p.lo_bits, nhi = (int)p.tw_hi.size() / 2;
@@ -518,7 +510,7 @@ int launch_fft(ta_ctx* ctx, std::vector<int>* grids) {
         if (dyn > (size_t)s.max_smem)
             return fail(ctx, TA_ERR_UNSUPPORTED, "FFT route: the twiddle tables for T=" + std::to_string(ctx->T) +
                                                      " do not fit in shared memory; use fft=False");
-        auto kern = in_smem ? k1_fft_acf<R, false, ST> : k1_fft_acf<R, true, ST>;
+        auto kern = in_smem ? k1_fft_acf<R, false> : k1_fft_acf<R, true>;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         int occ = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nthr, dyn));
@@ -537,7 +529,7 @@ int launch_fft(ta_ctx* ctx, std::vector<int>* grids) {
                 s.win_scratch_bytes = need;
             }
         }
-        K1Args<R, ST> a;
+        K1Args<R> a;
         a.t.T = (int)ctx->T; a.t.H = p.H; a.t.L = p.L; a.t.npasses = p.npasses;
         for (int q = 0; q < TA_MAX_PASSES; ++q) a.t.radix[q] = p.radix[q];
         a.t.lo_bits = p.lo_bits;
@@ -552,7 +544,7 @@ int launch_fft(ta_ctx* ctx, std::vector<int>* grids) {
         CK(cudaEventRecord(s.ev_ka, s.s_compute));
         for (const LaunchRange& rg : take_launch_ranges(s)) {
             if (rg.ready) CK(cudaStreamWaitEvent(s.s_compute, rg.ready, 0));
-            a.series = (const ST*)s.series + (size_t)rg.a0 * ctx->DS * ctx->Tld;
+            a.series = (const R*)s.series + (size_t)rg.a0 * ctx->DS * ctx->Tld;
             a.by_particle = s.by_particle + (size_t)rg.a0 * ctx->Tld;
             a.natoms = (int)rg.n;
             kern<<<(int)std::min<int64_t>(grid, rg.n), nthr, dyn, s.s_compute>>>(a);
@@ -566,42 +558,24 @@ int launch_fft(ta_ctx* ctx, std::vector<int>* grids) {
     return TA_OK;
 }
 
-template <int R1, typename RT, typename ST>
+template <int R1, typename RT>
 int launch_fft_fast_r1(ta_ctx* ctx, std::vector<int>* grids) {
     constexpr int NT = k1f_threads(R1);
-    const int smem_lockstep = k1f_smem_bytes(R1, k1f_prefetch(R1, (int)sizeof(RT)), (int)sizeof(RT), (int)sizeof(ST));
+    const int smem = k1f_smem_bytes(R1, k1f_prefetch(R1, (int)sizeof(RT)), (int)sizeof(RT));
     grids->assign(ctx->sh.size(), 0);
     for (size_t i = 0; i < ctx->sh.size(); ++i) {
         Shard& s = ctx->sh[i];
         if (s.natoms == 0) continue;
         CK(cudaSetDevice(s.dev));
-        void (*kern)(const K1FArgs<RT, ST>) = k1f_fft_acf<R1, RT, ST>;
-        int smem = smem_lockstep;
+        void (*kern)(const K1FArgs<RT>) = k1f_fft_acf<R1, RT>;
         if (smem > s.max_smem) return fail(ctx, TA_ERR_UNSUPPORTED, "three-pass FFT kernel needs more shared memory than the device has");
         int occ = 0;
-        bool pipelined = false;
-        if constexpr (k1p_supported(R1) && sizeof(RT) == 8 && sizeof(ST) == 4) {
-            // float series under FP64 arithmetic: the pipelined build (two FFT buffers, mbarriers instead of CTA barriers)
-            auto try_pipelined = [&](void (*kp)(const K1FArgs<double, float>), int smem_p) {
-                if (smem_p <= s.max_smem &&
-                    cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p) == cudaSuccess &&
-                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kp, NT, (size_t)smem_p) == cudaSuccess && occ >= 1) {
-                    kern = kp;
-                    smem = smem_p;
-                    pipelined = true;
-                } else cudaGetLastError();
-            };
-            if (!ctx->opt_lockstep_fft) {
-                if (ctx->opt_k1p_pref) try_pipelined(k1p_fft_acf<R1, true>, k1p_smem_bytes(R1, 8, 4, true));
-                else try_pipelined(k1p_fft_acf<R1, false>, k1p_smem_bytes(R1, 8, 4, false));
-            }
-        }
-        if (!pipelined) if constexpr (NT == 320 && sizeof(RT) == 8) {
+        if constexpr (NT == 320 && sizeof(RT) == 8) {
             // ten FP64 warps per SM: the build with the register cap stated outright (kernels.cuh); should a compiler
             // settle above what fits, the launch-bounds build of the same kernel takes over
-            cudaFuncSetAttribute(k1f_fft_acf_mr<R1, RT, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1f_fft_acf_mr<R1, RT, ST>, NT, (size_t)smem) == cudaSuccess && occ >= 1)
-                kern = k1f_fft_acf_mr<R1, RT, ST>;
+            cudaFuncSetAttribute(k1f_fft_acf_mr<R1, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1f_fft_acf_mr<R1, RT>, NT, (size_t)smem) == cudaSuccess && occ >= 1)
+                kern = k1f_fft_acf_mr<R1, RT>;
             else cudaGetLastError();
         }
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -611,25 +585,15 @@ int launch_fft_fast_r1(ta_ctx* ctx, std::vector<int>* grids) {
         (*grids)[i] = grid;
         int rc = ensure_partial(ctx, s, (size_t)grid);
         if (rc) return rc;
-        K1FArgs<RT, ST> a;
+        K1FArgs<RT> a;
         a.partial = s.partial;
         a.omega = (const cplx<RT>*)s.f_omega; a.tw2 = (const cplx<RT>*)s.f_tw2; a.map = s.f_map;
         a.wbase = (const cplx<RT>*)s.f_wbase; a.inv = (const RT*)s.f_inv;
         a.D = ctx->D; a.DS = ctx->DS; a.T = (int)ctx->T; a.nh = (int)((ctx->T + 1) / 2); a.Tld = ctx->Tld;
-        a.stagger = ctx->opt_k1p_stagger;
-#ifdef TA_EXPERIMENTS
-        long long* d_trace = nullptr;
-        const size_t trace_n = 16 * 96 * 8;
-        if (getenv("TA_B200_K1P_TRACE") && pipelined) {
-            CK(cudaMalloc(&d_trace, trace_n * sizeof(long long)));
-            CK(cudaMemset(d_trace, 0, trace_n * sizeof(long long)));
-            a.trace = d_trace;
-        }
-#endif
         CK(cudaEventRecord(s.ev_ka, s.s_compute));
         for (const LaunchRange& rg : take_launch_ranges(s)) {
             if (rg.ready) CK(cudaStreamWaitEvent(s.s_compute, rg.ready, 0));
-            a.series = (const ST*)s.series + (size_t)rg.a0 * ctx->DS * ctx->Tld;
+            a.series = (const RT*)s.series + (size_t)rg.a0 * ctx->DS * ctx->Tld;
             a.by_particle = s.by_particle + (size_t)rg.a0 * ctx->Tld;
             a.natoms = (int)rg.n;
             kern<<<(int)std::min<int64_t>(grid, rg.n), NT, smem, s.s_compute>>>(a);
@@ -638,31 +602,22 @@ int launch_fft_fast_r1(ta_ctx* ctx, std::vector<int>* grids) {
         }
         CK(cudaEventRecord(s.ev_kb, s.s_compute));
         s.kernel_timed = true;
-        ctx->k1_threads = NT; ctx->k1_smem = smem; ctx->k1_grid = grid; ctx->k1_pipelined = pipelined;
-#ifdef TA_EXPERIMENTS
-        if (d_trace) {
-            std::vector<long long> h(trace_n);
-            CK(cudaStreamSynchronize(s.s_compute));
-            CK(cudaMemcpy(h.data(), d_trace, trace_n * sizeof(long long), cudaMemcpyDeviceToHost));
-            cudaFree(d_trace);
-            if (FILE* f = fopen(getenv("TA_B200_K1P_TRACE"), "wb")) { fwrite(h.data(), sizeof(long long), trace_n, f); fclose(f); }
-        }
-#endif
+        ctx->k1_threads = NT; ctx->k1_smem = smem; ctx->k1_grid = grid;
     }
     return TA_OK;
 }
 
-template <typename RT, typename ST = RT>
+template <typename RT>
 int launch_fft_fast(ta_ctx* ctx, std::vector<int>* grids) {
     switch (ctx->fast_r1) {
-        case 4: return launch_fft_fast_r1<4, RT, ST>(ctx, grids);
-        case 6: return launch_fft_fast_r1<6, RT, ST>(ctx, grids);
-        case 8: return launch_fft_fast_r1<8, RT, ST>(ctx, grids);
-        case 10: return launch_fft_fast_r1<10, RT, ST>(ctx, grids);
-        case 12: return launch_fft_fast_r1<12, RT, ST>(ctx, grids);
-        case 16: return launch_fft_fast_r1<16, RT, ST>(ctx, grids);
-        case 20: return launch_fft_fast_r1<20, RT, ST>(ctx, grids);
-        case 24: return launch_fft_fast_r1<24, RT, ST>(ctx, grids);
+        case 4: return launch_fft_fast_r1<4, RT>(ctx, grids);
+        case 6: return launch_fft_fast_r1<6, RT>(ctx, grids);
+        case 8: return launch_fft_fast_r1<8, RT>(ctx, grids);
+        case 10: return launch_fft_fast_r1<10, RT>(ctx, grids);
+        case 12: return launch_fft_fast_r1<12, RT>(ctx, grids);
+        case 16: return launch_fft_fast_r1<16, RT>(ctx, grids);
+        case 20: return launch_fft_fast_r1<20, RT>(ctx, grids);
+        case 24: return launch_fft_fast_r1<24, RT>(ctx, grids);
     }
     return fail(ctx, TA_ERR_UNSUPPORTED, "no fast FFT instantiation for R1=" + std::to_string(ctx->fast_r1));
 }
@@ -670,12 +625,11 @@ int launch_fft_fast(ta_ctx* ctx, std::vector<int>* grids) {
 // the FFT autocorrelation pass of ta_vacf_fft / ta_helfand_fft: by_particle = sum_d acf_d, per-CTA partial rows
 int launch_k1(ta_ctx* ctx, std::vector<int>* grids) {
     const bool fp64 = ctx->precision == TA_PRECISION_FP64;
-    if (fp64 && ctx->narrow) return ctx->fast_r1 > 0 ? launch_fft_fast<double, float>(ctx, grids) : launch_fft<double, float>(ctx, grids);
     if (ctx->fast_r1 > 0) return fp64 ? launch_fft_fast<double>(ctx, grids) : launch_fft_fast<float>(ctx, grids);
     return fp64 ? launch_fft<double>(ctx, grids) : launch_fft<float>(ctx, grids);
 }
 
-template <typename R, int MODE, typename ST = R>
+template <typename R, int MODE>
 int launch_windowed(ta_ctx* ctx, double denom, std::vector<int>* grids) {
     const int T = (int)ctx->T;
     const int ne = win_smem_elems(T);
@@ -691,9 +645,9 @@ int launch_windowed(ta_ctx* ctx, double denom, std::vector<int>* grids) {
         // series + lag sums of one particle: shared memory when they fit, else a per-CTA global scratch area
         const bool in_smem = smem <= (size_t)s.max_smem;
         const size_t dyn_smem = in_smem ? smem : 0;
-        if (in_smem) CK(cudaFuncSetAttribute(k_windowed<R, MODE, false, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (in_smem) CK(cudaFuncSetAttribute(k_windowed<R, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;
-        if (in_smem) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_windowed<R, MODE, false, ST>, nthr, dyn_smem));
+        if (in_smem) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_windowed<R, MODE, false>, nthr, dyn_smem));
         else occ = 1;
         if (occ < 1) return fail(ctx, TA_ERR_UNSUPPORTED, "windowed kernel does not fit on an SM");
         // fewer than four particles per resident CTA: deal each particle's lag-block pairs to several CTAs, so that the
@@ -733,11 +687,11 @@ int launch_windowed(ta_ctx* ctx, double denom, std::vector<int>* grids) {
         CK(cudaEventRecord(s.ev_ka, s.s_compute));
         for (const LaunchRange& rg : take_launch_ranges(s)) {
             if (rg.ready) CK(cudaStreamWaitEvent(s.s_compute, rg.ready, 0));
-            a.series = (const ST*)s.series + (size_t)rg.a0 * ctx->DS * ctx->Tld;
+            a.series = (const R*)s.series + (size_t)rg.a0 * ctx->DS * ctx->Tld;
             a.by_particle = s.by_particle + (size_t)rg.a0 * ctx->Tld;
             a.natoms = (int)rg.n;
-            if (in_smem) k_windowed<R, MODE, false, ST><<<(int)std::min<int64_t>(grid, rg.n * nsplit), nthr, dyn_smem, s.s_compute>>>(a);
-            else k_windowed<R, MODE, true, ST><<<(int)std::min<int64_t>(grid, rg.n), nthr, 0, s.s_compute>>>(a);
+            if (in_smem) k_windowed<R, MODE, false><<<(int)std::min<int64_t>(grid, rg.n * nsplit), nthr, dyn_smem, s.s_compute>>>(a);
+            else k_windowed<R, MODE, true><<<(int)std::min<int64_t>(grid, rg.n), nthr, 0, s.s_compute>>>(a);
             CK(cudaGetLastError());
             ctx->launches++;
         }
@@ -756,13 +710,7 @@ int create_common(ta_ctx* ctx, int ndev, const int* devices) {
                         "); libta_b200 has no CPU fallback");
     if (ndev < 1) return fail(ctx, TA_ERR_INVALID, "ndev must be >= 1");
     // debugging knobs (see ta_ctx): read here, once, never on a launch path
-    if (const char* v = getenv("TA_B200_K1_PATH")) {
-        ctx->opt_general_fft = std::string(v) == "general";
-        ctx->opt_lockstep_fft = std::string(v) == "lockstep";
-    }
-    if (const char* v = getenv("TA_B200_SERIES")) ctx->opt_wide_series = std::string(v) == "wide";
-    if (const char* v = getenv("TA_B200_K1P_PREF")) ctx->opt_k1p_pref = atoi(v) != 0;
-    if (const char* v = getenv("TA_B200_K1P_STAGGER")) ctx->opt_k1p_stagger = atoi(v);
+    if (const char* v = getenv("TA_B200_K1_PATH")) ctx->opt_general_fft = std::string(v) == "general";
     if (const char* v = getenv("TA_B200_BULK_CHUNK")) ctx->opt_bulk_chunk = atoll(v);
     if (const char* v = getenv("TA_B200_HELFAND_FFT_THR")) ctx->opt_helfand_thr = atof(v);
     ctx->sh.resize(ndev);
@@ -948,7 +896,6 @@ int ta_stage_begin(ta_ctx* ctx, int64_t T, int64_t N, int D, const int* dims, in
     ctx->elt = (src_dtype == TA_DTYPE_F32) ? 4 : 8;
     ctx->n_fields = n_fields;
     ctx->precision = precision;
-    ctx->narrow = src_dtype == TA_DTYPE_F32 && n_fields == 1 && precision == TA_PRECISION_FP64 && !ctx->opt_wide_series;
     ctx->Tld = ((T + 15) / 16) * 16;
 
     // pinned slab ring: ~32 MB per slab, at most 512 frames
@@ -970,9 +917,8 @@ int ta_stage_begin(ta_ctx* ctx, int64_t T, int64_t N, int D, const int* dims, in
         CK(cudaMalloc(&s.ts_sum, ((size_t)ctx->Tld + 16) * sizeof(double)));
         CK(cudaMalloc(&s.ts_mean, (3 * (size_t)ctx->Tld + 16) * sizeof(double)));   // mean | times | running integral, out[2]
         if (s.natoms == 0) continue;
-        // the series are stored in the arithmetic type -- double, or float in the FP32 mode -- or as float under FP64
-        // arithmetic when that loses nothing (ctx->narrow)
-        const size_t ser_bytes = (size_t)s.natoms * ctx->DS * ctx->Tld * ((precision == TA_PRECISION_FP64 && !ctx->narrow) ? sizeof(double) : sizeof(float));
+        // the series are stored in the arithmetic type: double, or float in the FP32 mode
+        const size_t ser_bytes = (size_t)s.natoms * ctx->DS * ctx->Tld * (precision == TA_PRECISION_FP64 ? sizeof(double) : sizeof(float));
         const size_t out_bytes = (size_t)s.natoms * ctx->Tld * sizeof(double);
         cudaError_t e = cudaMalloc(&s.series, ser_bytes);
         if (e == cudaSuccess) e = cudaMalloc(&s.by_particle, out_bytes);
@@ -1134,9 +1080,8 @@ int ta_vacf_windowed(ta_ctx* ctx, double* ts_out) {
     if (rc) return rc;
     if (!ts_out) return fail(ctx, TA_ERR_INVALID, "ts_out is null");
     std::vector<int> grids;
-    if (ctx->precision != TA_PRECISION_FP64) rc = launch_windowed<float, TA_WIN_PRODUCT>(ctx, 1.0, &grids);
-    else rc = ctx->narrow ? launch_windowed<double, TA_WIN_PRODUCT, float>(ctx, 1.0, &grids)
-                          : launch_windowed<double, TA_WIN_PRODUCT>(ctx, 1.0, &grids);
+    rc = (ctx->precision == TA_PRECISION_FP64) ? launch_windowed<double, TA_WIN_PRODUCT>(ctx, 1.0, &grids)
+                                               : launch_windowed<float, TA_WIN_PRODUCT>(ctx, 1.0, &grids);
     if (rc) return rc;
     return finish_timeseries(ctx, grids, ts_out);
 }
@@ -1390,15 +1335,20 @@ int ta_probe_h2d(ta_ctx* ctx, uint64_t bytes, double* gbps) {
     CK(cudaEventCreate(&e1));
     CK(cudaMemcpyAsync(d, h, (size_t)bytes, cudaMemcpyHostToDevice, s.s_copy));    // warm-up
     CK(cudaStreamSynchronize(s.s_copy));
+    // twelve back-to-back copies: long enough (0.2 - 0.6 s at 1 GiB) that ranks probing at the same time overlap for
+    // nearly the whole timed region, whatever the skew of their allocations -- a SUSTAINED concurrent rate, which is
+    // what the staging path of a multi-rank run gets (three copies per rank mostly ran one rank after the other and
+    // reported 40 - 55 GB/s per rank on a host that sustains 23 GB/s per rank with eight ranks copying)
+    const int reps = 12;
     CK(cudaEventRecord(e0, s.s_copy));
-    for (int rep = 0; rep < 3; ++rep) CK(cudaMemcpyAsync(d, h, (size_t)bytes, cudaMemcpyHostToDevice, s.s_copy));
+    for (int rep = 0; rep < reps; ++rep) CK(cudaMemcpyAsync(d, h, (size_t)bytes, cudaMemcpyHostToDevice, s.s_copy));
     CK(cudaEventRecord(e1, s.s_copy));
     CK(cudaEventSynchronize(e1));
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(d); cudaFreeHost(h);
-    *gbps = 3.0 * (double)bytes / ((double)ms * 1e-3) / 1e9;
+    *gbps = (double)reps * (double)bytes / ((double)ms * 1e-3) / 1e9;
     return TA_OK;
 }
 

@@ -137,9 +137,7 @@ TA_HD double win_reduce16(const R* acc, bool take, int lane) {
 }
 
 struct WinArgs {
-    const void* series;     // [natoms][DS][Tld] of the storage type ST: the arithmetic type R, or float under FP64 arithmetic when the
-                            // source was float (the upcast of viscosity.py / velocityautocorr.py's np.zeros f64 arrays is exact, so it
-                            // can happen here instead of in HBM); rows 0 .. D-1 are used
+    const void* series;     // [natoms][DS][Tld] of the arithmetic type R (double, or float in the FP32 mode); rows 0 .. D-1 are used
     double* by_particle;    // [natoms][Tld]
     double* partial;        // [nblk][Tld]
     int natoms, D, DS, T;
@@ -162,7 +160,7 @@ struct WinArgs {
 //   MODE = TA_WIN_PRODUCT: vacf[k] = sum_d sum_i g_d[i] g_d[i+k] / (T-k)
 //   MODE = TA_WIN_SQDIFF : visc[k] = sum_d sum_i (g_d[i]-g_d[i+k])^2 / (D (T-k)) / denom
 // ---------------------------------------------------------------------------
-template <typename R, int MODE, class Ctx, bool SCRATCH = false, typename ST = R>
+template <typename R, int MODE, class Ctx, bool SCRATCH = false>
 TA_HD void win_body(const WinArgs& A, unsigned char* smem_raw, int tid, int nthr, int bid, int nblk) {
     const int T = A.T;
     const int ne = win_smem_elems(T);
@@ -180,11 +178,11 @@ TA_HD void win_body(const WinArgs& A, unsigned char* smem_raw, int tid, int nthr
         const int a = (int)(u / nsplit), part = (int)(u % nsplit);
         for (int k = tid; k < T; k += nthr) res[k] = 0.0;
         for (int d = 0; d < A.D; ++d) {
-            const ST* ser = reinterpret_cast<const ST*>(A.series) + ((size_t)a * A.DS + d) * A.Tld;
+            const R* ser = reinterpret_cast<const R*>(A.series) + ((size_t)a * A.DS + d) * A.Tld;
             Ctx::sync();   // previous series fully consumed
             for (int x = tid; x < ne; x += nthr) S[x] = (R)0;
             Ctx::sync();
-            for (int x = tid; x < T; x += nthr) S[win_addr(x)] = (R)ser[x];
+            for (int x = tid; x < T; x += nthr) S[win_addr(x)] = ser[x];
             Ctx::sync();
             // ---- unmasked tiles: a warp per block pair, lanes split between the two blocks
             for (int pair = part * nwarps + warp; pair < npairs; pair += nwarps * nsplit) {
