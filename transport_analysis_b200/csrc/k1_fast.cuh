@@ -110,7 +110,9 @@ TA_HD void k1f_p1_twiddles(C om, int r, C* e, C* g) {
 // device these are the hardware's, in tests/emu they are cooperative-fiber versions so the very same code runs on
 // the CPU.
 // ---------------------------------------------------------------------------
-template <int R1, int NT, class Ctx, typename RT, bool PREF>
+// PART = false: the per-CTA particle-sum row is not wanted (ta_helfand_fft: K5 forms its own sums from the finished rows),
+// so the output stage neither reads nor writes it -- a third of that stage's L2 traffic.
+template <int R1, int NT, class Ctx, typename RT, bool PREF, bool PART = true>
 TA_HD void k1f_body(const K1FArgs<RT>& A, unsigned char* smem_raw, int tid, int bid, int nblk) {
     using C = cplx<RT>;
     constexpr int H = 256 * R1;
@@ -347,7 +349,8 @@ TA_HD void k1f_body(const K1FArgs<RT>& A, unsigned char* smem_raw, int tid, int 
                         for (int i = 0; i < nq; ++i) {
                             const int n = j + 256 * (q0 + i);
                             const int nc = n < nh ? n : nh - 1;      // clamped: the loads stay branch-free
-                            a[i] = Ctx::ld_stream(row + nc); ps[i] = Ctx::ld_stream(part + nc);
+                            a[i] = Ctx::ld_stream(row + nc);
+                            if (PART) ps[i] = Ctx::ld_stream(part + nc);
                             sc[i] = inv2[nc];
                         }
 #pragma unroll
@@ -358,7 +361,7 @@ TA_HD void k1f_body(const K1FArgs<RT>& A, unsigned char* smem_raw, int tid, int 
                                 const cd o = cmake<double>((double)(((RT)a[i].x + v1.x) * sc[i].x),
                                                            (double)(((RT)a[i].y + v1.y) * sc[i].y));
                                 row[n] = o;
-                                part[n] = cmake<double>(ps[i].x + o.x, ps[i].y + o.y);
+                                if (PART) part[n] = cmake<double>(ps[i].x + o.x, ps[i].y + o.y);
                             }
                         }
                     });

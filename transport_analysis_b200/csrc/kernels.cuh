@@ -226,12 +226,12 @@ struct DevCtx {
 };
 
 // One kernel per (R1, arithmetic type).  NT = 16 R1 threads; the bulk series prefetch where k1f_prefetch says so.
-template <int R1, typename RT>
+template <int R1, typename RT, bool PART = true>
 __global__ void __launch_bounds__(k1f_threads(R1), k1f_min_blocks(k1f_threads(R1), (int)sizeof(RT)))
 k1f_fft_acf(const K1FArgs<RT> args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    k1f_body<R1, k1f_threads(R1), DevCtx, RT, k1f_prefetch(R1, (int)sizeof(RT))>(args, smem_raw, (int)threadIdx.x, (int)blockIdx.x,
-                                                                                 (int)gridDim.x);
+    k1f_body<R1, k1f_threads(R1), DevCtx, RT, k1f_prefetch(R1, (int)sizeof(RT)), PART>(args, smem_raw, (int)threadIdx.x, (int)blockIdx.x,
+                                                                                       (int)gridDim.x);
 }
 
 // The FP64 kernel of ten warps (R1 = 20) with the register cap stated outright instead of derived from launch bounds.
@@ -240,12 +240,12 @@ k1f_fft_acf(const K1FArgs<RT> args) {
 // 16-32 B of spills, __maxnreg__(184) 166 registers and none -- 24.2 -> 23.5 ms at 100k x 10k (caps 152 / 160 / 168 /
 // 176 / 184: 24.21 / 24.08 / 23.66 / 23.52 / 23.46 ms; 200 does not fit).
 constexpr int K1F_MAXREG = 184;
-template <int R1, typename RT>
+template <int R1, typename RT, bool PART = true>
 __global__ void __maxnreg__(K1F_MAXREG)
 k1f_fft_acf_mr(const K1FArgs<RT> args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    k1f_body<R1, k1f_threads(R1), DevCtx, RT, k1f_prefetch(R1, (int)sizeof(RT))>(args, smem_raw, (int)threadIdx.x, (int)blockIdx.x,
-                                                                                 (int)gridDim.x);
+    k1f_body<R1, k1f_threads(R1), DevCtx, RT, k1f_prefetch(R1, (int)sizeof(RT)), PART>(args, smem_raw, (int)threadIdx.x, (int)blockIdx.x,
+                                                                                       (int)gridDim.x);
 }
 
 // ---------------------------------------------------------------------------

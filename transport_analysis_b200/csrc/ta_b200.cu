@@ -558,7 +558,8 @@ int launch_fft(ta_ctx* ctx, std::vector<int>* grids) {
     return TA_OK;
 }
 
-template <int R1, typename RT>
+// PART = false (FP64 only): without the per-CTA particle sums (ta_helfand_fft does not use them)
+template <int R1, typename RT, bool PART = true>
 int launch_fft_fast_r1(ta_ctx* ctx, std::vector<int>* grids) {
     constexpr int NT = k1f_threads(R1);
     const int smem = k1f_smem_bytes(R1, k1f_prefetch(R1, (int)sizeof(RT)), (int)sizeof(RT));
@@ -567,15 +568,15 @@ int launch_fft_fast_r1(ta_ctx* ctx, std::vector<int>* grids) {
         Shard& s = ctx->sh[i];
         if (s.natoms == 0) continue;
         CK(cudaSetDevice(s.dev));
-        void (*kern)(const K1FArgs<RT>) = k1f_fft_acf<R1, RT>;
+        void (*kern)(const K1FArgs<RT>) = k1f_fft_acf<R1, RT, PART>;
         if (smem > s.max_smem) return fail(ctx, TA_ERR_UNSUPPORTED, "three-pass FFT kernel needs more shared memory than the device has");
         int occ = 0;
         if constexpr (NT == 320 && sizeof(RT) == 8) {
             // ten FP64 warps per SM: the build with the register cap stated outright (kernels.cuh); should a compiler
             // settle above what fits, the launch-bounds build of the same kernel takes over
-            cudaFuncSetAttribute(k1f_fft_acf_mr<R1, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1f_fft_acf_mr<R1, RT>, NT, (size_t)smem) == cudaSuccess && occ >= 1)
-                kern = k1f_fft_acf_mr<R1, RT>;
+            cudaFuncSetAttribute(k1f_fft_acf_mr<R1, RT, PART>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1f_fft_acf_mr<R1, RT, PART>, NT, (size_t)smem) == cudaSuccess && occ >= 1)
+                kern = k1f_fft_acf_mr<R1, RT, PART>;
             else cudaGetLastError();
         }
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -607,24 +608,25 @@ int launch_fft_fast_r1(ta_ctx* ctx, std::vector<int>* grids) {
     return TA_OK;
 }
 
-template <typename RT>
+template <typename RT, bool PART = true>
 int launch_fft_fast(ta_ctx* ctx, std::vector<int>* grids) {
     switch (ctx->fast_r1) {
-        case 4: return launch_fft_fast_r1<4, RT>(ctx, grids);
-        case 6: return launch_fft_fast_r1<6, RT>(ctx, grids);
-        case 8: return launch_fft_fast_r1<8, RT>(ctx, grids);
-        case 10: return launch_fft_fast_r1<10, RT>(ctx, grids);
-        case 12: return launch_fft_fast_r1<12, RT>(ctx, grids);
-        case 16: return launch_fft_fast_r1<16, RT>(ctx, grids);
-        case 20: return launch_fft_fast_r1<20, RT>(ctx, grids);
-        case 24: return launch_fft_fast_r1<24, RT>(ctx, grids);
+        case 4: return launch_fft_fast_r1<4, RT, PART>(ctx, grids);
+        case 6: return launch_fft_fast_r1<6, RT, PART>(ctx, grids);
+        case 8: return launch_fft_fast_r1<8, RT, PART>(ctx, grids);
+        case 10: return launch_fft_fast_r1<10, RT, PART>(ctx, grids);
+        case 12: return launch_fft_fast_r1<12, RT, PART>(ctx, grids);
+        case 16: return launch_fft_fast_r1<16, RT, PART>(ctx, grids);
+        case 20: return launch_fft_fast_r1<20, RT, PART>(ctx, grids);
+        case 24: return launch_fft_fast_r1<24, RT, PART>(ctx, grids);
     }
     return fail(ctx, TA_ERR_UNSUPPORTED, "no fast FFT instantiation for R1=" + std::to_string(ctx->fast_r1));
 }
 
 // the FFT autocorrelation pass of ta_vacf_fft / ta_helfand_fft: by_particle = sum_d acf_d, per-CTA partial rows
-int launch_k1(ta_ctx* ctx, std::vector<int>* grids) {
+int launch_k1(ta_ctx* ctx, std::vector<int>* grids, bool with_partial = true) {
     const bool fp64 = ctx->precision == TA_PRECISION_FP64;
+    if (ctx->fast_r1 > 0 && fp64 && !with_partial) return launch_fft_fast<double, false>(ctx, grids);
     if (ctx->fast_r1 > 0) return fp64 ? launch_fft_fast<double>(ctx, grids) : launch_fft_fast<float>(ctx, grids);
     return fp64 ? launch_fft<double>(ctx, grids) : launch_fft<float>(ctx, grids);
 }
@@ -1118,7 +1120,7 @@ int ta_helfand_fft(ta_ctx* ctx, const double* volumes, double boltzmann, double 
             return fail(ctx, TA_ERR_UNSUPPORTED, "FFT Helfand route: T=" + std::to_string(ctx->T) + " does not fit shared memory");
     if ((rc = ensure_fft_plan(ctx))) return rc;
     std::vector<int> grids;
-    if ((rc = launch_k1(ctx, &grids))) return rc;                 // by_particle = sum_d acf_d
+    if ((rc = launch_k1(ctx, &grids, /*with_partial=*/false))) return rc;   // by_particle = sum_d acf_d; K5 forms the particle sums
     // K5 forms S1 - 2 S2 and lists the lags whose result is not good to 1e-10 (cancellation); K6 evaluates those exactly.
     // thr = C eps / tol: C = 100 + T / 100 bounds the error constant of S1 - 2 S2 (FFT autocorrelation + prefix sums;
     // measured 9 - 20 on random, random-walk, ramp, spike, offset and piecewise-constant moments, 18 - 33 on smooth ones:
