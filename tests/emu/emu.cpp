@@ -93,7 +93,7 @@ static int run_win(const double* series_f64, int T, int D, int Tld, int mode, in
     return 0;
 }
 
-template <int R1, typename RT>
+template <int R1, typename RT, bool TMEM = false>
 static int run_k1fast(const double* series_f64, int T, int D, int Tld, int natoms, int nblk, double* by_particle,
                       double* partial) {
     K1FastPlan p;
@@ -114,7 +114,7 @@ static int run_k1fast(const double* series_f64, int T, int D, int Tld, int natom
     std::vector<unsigned char> smem(k1f_smem_bytes(R1, PREF, (int)sizeof(RT)) + 64);
     unsigned char* sm = smem.data() + (16 - ((uintptr_t)smem.data() & 15)) % 16;
     for (int bid = 0; bid < nblk; ++bid)
-        emu::run_cta(k1f_threads(R1), [&](int tid) { k1f_body<R1, k1f_threads(R1), emu::EmuCtx, RT, PREF>(a, sm, tid, bid, nblk); });
+        emu::run_cta(k1f_threads(R1), [&](int tid) { k1f_body<R1, k1f_threads(R1), emu::EmuCtx, RT, PREF, true, TMEM>(a, sm, tid, bid, nblk); });
     return 0;
 }
 
@@ -135,9 +135,15 @@ static int run_k1fast_any(const double* series, int T, int D, int Tld, int natom
 
 extern "C" {
 int emu_k1fast_r1(int T) { return k1f_choose_r1(T); }
-// the three-pass kernel body as shipped for (R1, precision): use_f32 = 0 FP64, 1 FP32 (float series, float arithmetic)
+// the three-pass kernel body as shipped for (R1, precision): use_f32 = 0 FP64, 1 FP32 (float series, float arithmetic),
+// 2 FP64 with the tensor-memory output stage (R1 = 16, 20)
 int emu_k1fast(const double* series, int T, int D, int Tld, int natoms, int nblk, int R1, int use_f32, double* by_particle,
                double* partial) {
+    if (use_f32 == 2) {     // FP64 with the output stage's per-thread streams in tensor memory (the R1 the library ships it for)
+        if (R1 == 16) return run_k1fast<16, double, true>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        if (R1 == 20) return run_k1fast<20, double, true>(series, T, D, Tld, natoms, nblk, by_particle, partial);
+        return -1;
+    }
     return use_f32 ? run_k1fast_any<float>(series, T, D, Tld, natoms, nblk, R1, by_particle, partial)
                    : run_k1fast_any<double>(series, T, D, Tld, natoms, nblk, R1, by_particle, partial);
 }

@@ -24,6 +24,8 @@ struct Cta {
     int bar_count = 0, bar_gen = 0;
     // named barriers (bar.sync / bar.arrive id, count)
     int nb_count[16] = {0}, nb_gen[16] = {0};
+    // tensor memory as the kernels use it: 512 32-bit columns of each thread's own lane
+    std::vector<double> tmem;       // [nthreads][256]
     // per-warp shuffle state
     std::vector<double> slot;       // [nthreads]
     std::vector<int> w_count, w_gen; // [nwarps]
@@ -55,6 +57,7 @@ inline void run_cta(int nthreads, std::function<void(int)> body, size_t stack_by
     c.stacks.resize(nthreads);
     c.done.assign(nthreads, 0);
     c.slot.assign(nthreads, 0.0);
+    c.tmem.assign((size_t)nthreads * 256, -1.2345e300);      // uninitialised columns read back as nonsense
     const int nwarps = (nthreads + 31) / 32;
     c.w_count.assign(nwarps, 0);
     c.w_gen.assign(nwarps, 0);
@@ -167,6 +170,29 @@ struct EmuCtx {
         mbar_arrive(bar);
     }
     static unsigned atomic_inc_acq_rel(unsigned* p) { return (*p)++; }
+    // tensor memory (tcgen05.alloc / st / ld / dealloc): the address carries the lane quarter of the calling warp in
+    // bits 16-31 -- checked, because on the device a warp cannot reach another quarter -- and the column in bits 0-15
+    static uint32_t tmem_alloc(uint32_t* slot, int) { *slot = 0; sync_block(); return *slot; }
+    static void tmem_free(uint32_t, int) { sync_block(); }
+    static double* tmem_cols(uint32_t taddr) {
+        Cta* c = active();
+        const int tid = c->current;
+        const uint32_t lane0 = taddr >> 16, col = taddr & 0xffffu;
+        if (lane0 != (uint32_t)(((tid >> 5) & 3) * 32) || col % 4 != 0 || col + 16 > 512) {
+            fprintf(stderr, "emu: thread %d addresses tensor memory lane %u column %u\n", tid, lane0, col);
+            abort();
+        }
+        return &c->tmem[(size_t)tid * 256 + col / 2];
+    }
+    template <class V> static void tmem_st4(uint32_t taddr, const V (&v)[4]) {
+        double* p = tmem_cols(taddr);
+        for (int i = 0; i < 4; ++i) { p[2 * i] = (double)v[i].x; p[2 * i + 1] = (double)v[i].y; }
+    }
+    template <class V> static void tmem_ld4(uint32_t taddr, V (&v)[4]) {
+        const double* p = tmem_cols(taddr);
+        for (int i = 0; i < 4; ++i) { v[i].x = p[2 * i]; v[i].y = p[2 * i + 1]; }
+    }
+    static void tmem_wait_st() {}
     static void delay(unsigned clocks) { for (unsigned i = 0; i < clocks / 64; ++i) emu::yield_now(); }
     template <class V> static V ld_stream(const V* p) { return *p; }
 };

@@ -173,3 +173,20 @@ def test_three_pass_kernel_at_the_ends_of_every_length_range(emu, T, R1):
     bp, part = emu_fast(emu, x, 1, R1)
     assert_close_normwise(bp[0], oracle.tidynamics_acf(x[:, 0, :]), 1e-12, f"T={T} R1={R1}")
     np.testing.assert_array_equal(part[0], bp[0])
+
+
+@pytest.mark.parametrize("T,D,N,nblk", [(10000, 3, 1, 1), (10000, 3, 5, 2), (9999, 2, 3, 1), (8192, 1, 4, 2), (7000, 3, 2, 3),
+                                        (8000, 2, 3, 1), (10240, 1, 1, 1), (6200, 3, 2, 1)])
+def test_tensor_memory_output_stage_gives_the_bits_of_the_global_one(emu, T, D, N, nblk):
+    """k1f_body<..., TMEM = true>: parked V_0, particle sums and the 1/(L(T-k)) table in each thread's own tensor-memory
+    columns instead of global memory.  Same arithmetic in the same order: rows and per-CTA particle sums bit for bit, for
+    every D, several particles per CTA, CTAs without work, odd T (a last complex value with an empty imaginary lag) and
+    series that fill H exactly."""
+    x = np.random.default_rng(T + D + N).standard_normal((T, N, D))
+    R1 = emu.emu_k1fast_r1(T)
+    assert R1 in (16, 20)
+    ref_bp, ref_part = emu_fast(emu, x, nblk, R1)
+    bp, part = emu_fast(emu, x, nblk, R1, f32=2)
+    assert np.array_equal(bp, ref_bp)
+    assert np.array_equal(part, ref_part)
+    assert_close_normwise(bp[0], oracle.tidynamics_acf(x[:, 0, :]), 1e-12, f"T={T}")

@@ -318,6 +318,34 @@ def test_fft_fast_path_vs_oracle_and_general_kernel(T, N, dim, monkeypatch):
     assert_close_normwise(g.results.timeseries, v.results.timeseries, 1e-11, "fast vs general kernel, timeseries")
 
 
+@pytest.mark.parametrize("T,N,dim", [(10000, 700, "xyz"), (8000, 450, "xz"), (6200, 333, "y")])
+def test_tensor_memory_output_stage_vs_global_one_and_across_launches(T, N, dim, monkeypatch):
+    """R1 = 16 / 20 in FP64: the output stage keeps the parked V_0, the particle sums and the 1/(L(T-k)) table in tensor
+    memory (tcgen05.st / ld on each thread's own columns).  Against the build that sends them through L2
+    (TA_B200_K1_PATH=notmem): per-particle rows bit for bit; the timeseries too when one launch does the shard, and up to
+    the order of the sums when the compute call launches once per staging chunk (each launch ADDS its sums to the global
+    partial rows)."""
+    vel, _ = random_trajectory(T, N, seed=T + N, rho=0.7)
+    u = make_universe(None, vel)
+    v = VACF(u.atoms, dim_type=dim, fft=True).run()
+    assert v._ctx.fft_plan_info()["radices"][0] in (16, 20)
+    cols, _ = oracle.parse_dim_type(dim)
+    ref_bp, _ = oracle.vacf_fft(_f64(vel)[:, :4, cols])
+    assert_close_normwise(v.results.vacf_by_particle[:, :4], ref_bp, TOL64, "tensor-memory build vs oracle")
+    assert_close_normwise(v.results.timeseries, v.results.vacf_by_particle.mean(axis=1), 1e-13, "timeseries = particle mean")
+    monkeypatch.setenv("TA_B200_BULK_CHUNK", "148")
+    c = VACF(u.atoms, dim_type=dim, fft=True).run()
+    assert c._ctx.launch_count() >= 2 * (-(-N // 148))
+    assert np.array_equal(c.results.vacf_by_particle, v.results.vacf_by_particle)
+    assert_allclose(c.results.timeseries, v.results.timeseries, rtol=1e-13, atol=1e-15)
+    assert_close_normwise(c.results.timeseries, c.results.vacf_by_particle.mean(axis=1), 1e-13, "chunked: timeseries = particle mean")
+    monkeypatch.delenv("TA_B200_BULK_CHUNK")
+    monkeypatch.setenv("TA_B200_K1_PATH", "notmem")
+    g = VACF(u.atoms, dim_type=dim, fft=True).run()
+    assert np.array_equal(g.results.vacf_by_particle, v.results.vacf_by_particle)
+    assert np.array_equal(g.results.timeseries, v.results.timeseries)
+
+
 @pytest.mark.parametrize("T,want", [(1000, None), (2000, [4, 16, 16]), (5000, [10, 16, 16]), (10000, [20, 16, 16]),
                                     (12000, [24, 16, 16]), (13000, None)])
 def test_fft_default_kernel_choice(T, want):

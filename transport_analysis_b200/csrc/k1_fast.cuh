@@ -112,9 +112,17 @@ TA_HD void k1f_p1_twiddles(C om, int r, C* e, C* g) {
 // ---------------------------------------------------------------------------
 // PART = false: the per-CTA particle-sum row is not wanted (ta_helfand_fft: K5 forms its own sums from the finished rows),
 // so the output stage neither reads nor writes it -- a third of that stage's L2 traffic.
-template <int R1, int NT, class Ctx, typename RT, bool PREF, bool PART = true>
+// TMEM = true (FP64, one P1 column per thread: NT >= 256, R1 a multiple of 4): the three per-thread streams of the output stage
+// live in TENSOR MEMORY instead of going through L2 -- the parked V_0 of residue 0, the CTA's particle-sum row and the
+// 1/(L(T-k)) table, 4 R1 32-bit columns each.  Every P1' thread only ever touches the values of its own column j, which is
+// exactly what tcgen05.st / tcgen05.ld offer (a thread reads and writes its own TMEM lane; a warp owns the 32 lanes of
+// its quarter, the two P1 warps of a quarter take 256 columns each).  The stage then moves 80 KB per particle between the SM
+// and L2 (the finished row) instead of 480 KB, and has no L2 round trip to wait for.
+template <int R1, int NT, class Ctx, typename RT, bool PREF, bool PART = true, bool TMEM = false>
 TA_HD void k1f_body(const K1FArgs<RT>& A, unsigned char* smem_raw, int tid, int bid, int nblk) {
     using C = cplx<RT>;
+    static_assert(!TMEM || (PART && PREF && sizeof(RT) == 8 && NT >= 256 && R1 % 4 == 0 && 12 * R1 <= 256),
+                  "tensor-memory build: FP64, one P1 column per thread, three 4 R1-column arrays in a 256-column half");
     constexpr int H = 256 * R1;
     constexpr int NV = 16 * R1;          // radix-16 butterflies per pass ("virtual threads")
     constexpr int NB = (NV + NT - 1) / NT;   // butterfly rounds of P2 / P3; a thread owns vt = tid + it NT < NV
@@ -134,6 +142,31 @@ TA_HD void k1f_body(const K1FArgs<RT>& A, unsigned char* smem_raw, int tid, int 
     Ctx::sync();
 
     const int nh = A.nh;
+    // TMEM: 512 columns allocated by warp 0; this thread's slice = lane quarter of its warp, column half of its warp pair;
+    // columns [0, 4 R1) parked V_0, [4 R1, 8 R1) particle sums, [8 R1, 12 R1) 1 / (L (T - k)), one complex double = 4 columns
+    uint32_t tm_base = 0, tm = 0;
+    constexpr uint32_t TM_PART = 4 * R1, TM_INV = 8 * R1;
+    if (TMEM) {
+        tm_base = Ctx::tmem_alloc(reinterpret_cast<uint32_t*>(mbar + 2), tid);
+        tm = tm_base + ((uint32_t)(((tid >> 5) & 3) * 32) << 16) + (uint32_t)((tid >> 7) & 1) * 256u;
+        if (tid < 256) {
+            const C* inv2i = reinterpret_cast<const C*>(A.inv);
+            static_for<0, R1 / 4>([&](auto ic) {
+                constexpr int c = decltype(ic)::value;
+                cd z[4], sc[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int n = tid + 256 * (4 * c + i);
+                    z[i] = cmake<double>(0.0, 0.0);
+                    sc[i] = z[i];
+                    if (n < nh) { const C v = inv2i[n]; sc[i] = cmake<double>((double)v.x, (double)v.y); }   // 0 beyond the series: nothing is added there
+                }
+                Ctx::tmem_st4(tm + TM_PART + 16 * c, z);
+                Ctx::tmem_st4(tm + TM_INV + 16 * c, sc);
+            });
+            Ctx::tmem_wait_st();
+        }
+    }
     // bytes of one series the bulk copy moves: nh complex values, rounded up to the 16 bytes the engine works in
     // (FP32: the extra 8 bytes are the zero padding of the row, Tld is a multiple of 16 elements)
     const unsigned ser_bytes = ((unsigned)nh * (unsigned)sizeof(C) + 15u) & ~15u;
@@ -324,7 +357,45 @@ TA_HD void k1f_body(const K1FArgs<RT>& A, unsigned char* smem_raw, int tid, int 
                     });
                 }
                 // x[q] = V_r[n] (r = 1: already multiplied by conj(w_L^{2n})), n = j + 256 q
-                if (r == 0) {
+                if (TMEM) {
+                    if (r == 0) {
+                        // parked in this thread's tensor-memory columns until residue 1 is through
+                        static_for<0, R1 / 4>([&](auto ic) {
+                            constexpr int c = decltype(ic)::value;
+                            cd v[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) v[i] = cmake<double>((double)x[4 * c + i].x, (double)x[4 * c + i].y);
+                            Ctx::tmem_st4(tm + 16 * c, v);
+                        });
+                        Ctx::tmem_wait_st();
+                    } else {
+                        static_for<0, R1 / 4>([&](auto ic) {
+                            constexpr int c = decltype(ic)::value;
+                            // one 16-column load at a time (each returns in ~12 clocks): the chunk's four values of x[] are
+                            // finished in place, so no more than 16 extra registers are live beside x[]
+                            cd t[4];
+                            Ctx::tmem_ld4(tm + 16 * c, t);                       // parked V_0
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                x[4 * c + i] = cmake<RT>((RT)t[i].x + x[4 * c + i].x, (RT)t[i].y + x[4 * c + i].y);
+                            Ctx::tmem_ld4(tm + TM_INV + 16 * c, t);              // 1 / (L (T - k)), 0 beyond the series
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int n = j + 256 * (4 * c + i);
+                                x[4 * c + i] = cmake<RT>(x[4 * c + i].x * (RT)t[i].x, x[4 * c + i].y * (RT)t[i].y);
+                                if (n < nh) row[n] = cmake<double>((double)x[4 * c + i].x, (double)x[4 * c + i].y);
+                            }
+                            Ctx::tmem_ld4(tm + TM_PART + 16 * c, t);             // particle sums
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int n = j + 256 * (4 * c + i);
+                                if (n < nh) t[i] = cmake<double>(t[i].x + (double)x[4 * c + i].x, t[i].y + (double)x[4 * c + i].y);
+                            }
+                            Ctx::tmem_st4(tm + TM_PART + 16 * c, t);
+                        });
+                        Ctx::tmem_wait_st();
+                    }
+                } else if (r == 0) {
 #pragma unroll
                     for (int q = 0; q < R1; ++q) {
                         const int n = j + 256 * q;
@@ -370,6 +441,24 @@ TA_HD void k1f_body(const K1FArgs<RT>& A, unsigned char* smem_raw, int tid, int 
             // no barrier here: P1 of the next chain writes exactly the elements this
             // thread has just read in P1'
         }
+    }
+    if (TMEM) {
+        // add the particle sums of this launch to the CTA's global partial row (the host zeroed it before the first launch
+        // of the compute call; a call that follows ta_stage_bulk launches once per staging chunk), then give the tensor
+        // memory back
+        if (tid < 256) {
+            static_for<0, R1 / 4>([&](auto ic) {
+                constexpr int c = decltype(ic)::value;
+                cd ps[4];
+                Ctx::tmem_ld4(tm + TM_PART + 16 * c, ps);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int n = tid + 256 * (4 * c + i);
+                    if (n < nh) { const cd g0 = part[n]; part[n] = cmake<double>(g0.x + ps[i].x, g0.y + ps[i].y); }
+                }
+            });
+        }
+        Ctx::tmem_free(tm_base, tid);
     }
 }
 

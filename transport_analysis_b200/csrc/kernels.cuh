@@ -212,6 +212,64 @@ struct DevCtx {
                      ::"r"(d), "l"(src), "r"(bytes), "r"(a) : "memory");
 #endif
     }
+    // ---- tensor memory as a per-thread scratchpad (k1f_body<..., TMEM = true>)
+    // 512 columns for the CTA: warp 0 allocates, everybody learns the base address.  Called by ALL threads.
+    static TA_HD uint32_t tmem_alloc(uint32_t* slot, int tid) {
+#if defined(__CUDA_ARCH__)
+        if ((tid >> 5) == 0) {
+            const unsigned a = (unsigned)__cvta_generic_to_shared(slot);
+            const unsigned ncols = 512u;
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(a), "r"(ncols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        return *reinterpret_cast<volatile uint32_t*>(slot);
+#else
+        return 0;
+#endif
+    }
+    static TA_HD void tmem_free(uint32_t base, int tid) {
+#if defined(__CUDA_ARCH__)
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if ((tid >> 5) == 0) {
+            const unsigned ncols = 512u;
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(ncols) : "memory");
+        }
+#endif
+    }
+    // four complex doubles = 16 columns of the calling thread's own lane (whole warps only: .sync.aligned)
+    static TA_HD void tmem_st4(uint32_t taddr, const cd (&v)[4]) {
+#if defined(__CUDA_ARCH__)
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                     ::"r"(taddr),
+                       "r"(__double2loint(v[0].x)), "r"(__double2hiint(v[0].x)), "r"(__double2loint(v[0].y)), "r"(__double2hiint(v[0].y)),
+                       "r"(__double2loint(v[1].x)), "r"(__double2hiint(v[1].x)), "r"(__double2loint(v[1].y)), "r"(__double2hiint(v[1].y)),
+                       "r"(__double2loint(v[2].x)), "r"(__double2hiint(v[2].x)), "r"(__double2loint(v[2].y)), "r"(__double2hiint(v[2].y)),
+                       "r"(__double2loint(v[3].x)), "r"(__double2hiint(v[3].x)), "r"(__double2loint(v[3].y)), "r"(__double2hiint(v[3].y))
+                     : "memory");
+#endif
+    }
+    // load + wait in one statement: the registers are valid when it returns
+    static TA_HD void tmem_ld4(uint32_t taddr, cd (&v)[4]) {
+#if defined(__CUDA_ARCH__)
+        int w[16];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+                     "tcgen05.wait::ld.sync.aligned;"
+                     : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]),
+                       "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+                     : "r"(taddr) : "memory");
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = cmake<double>(__hiloint2double(w[4 * i + 1], w[4 * i]), __hiloint2double(w[4 * i + 3], w[4 * i + 2]));
+#endif
+    }
+    static TA_HD void tmem_wait_st() {
+#if defined(__CUDA_ARCH__)
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#endif
+    }
     static TA_HD void mbar_wait(unsigned long long* bar, unsigned parity) {
 #if defined(__CUDA_ARCH__)
         const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
@@ -226,12 +284,12 @@ struct DevCtx {
 };
 
 // One kernel per (R1, arithmetic type).  NT = 16 R1 threads; the bulk series prefetch where k1f_prefetch says so.
-template <int R1, typename RT, bool PART = true>
+template <int R1, typename RT, bool PART = true, bool TMEM = false>
 __global__ void __launch_bounds__(k1f_threads(R1), k1f_min_blocks(k1f_threads(R1), (int)sizeof(RT)))
 k1f_fft_acf(const K1FArgs<RT> args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    k1f_body<R1, k1f_threads(R1), DevCtx, RT, k1f_prefetch(R1, (int)sizeof(RT)), PART>(args, smem_raw, (int)threadIdx.x, (int)blockIdx.x,
-                                                                                       (int)gridDim.x);
+    k1f_body<R1, k1f_threads(R1), DevCtx, RT, k1f_prefetch(R1, (int)sizeof(RT)), PART, TMEM>(args, smem_raw, (int)threadIdx.x,
+                                                                                             (int)blockIdx.x, (int)gridDim.x);
 }
 
 // The FP64 kernel of ten warps (R1 = 20) with the register cap stated outright instead of derived from launch bounds.
@@ -240,12 +298,12 @@ k1f_fft_acf(const K1FArgs<RT> args) {
 // 16-32 B of spills, __maxnreg__(184) 166 registers and none -- 24.2 -> 23.5 ms at 100k x 10k (caps 152 / 160 / 168 /
 // 176 / 184: 24.21 / 24.08 / 23.66 / 23.52 / 23.46 ms; 200 does not fit).
 constexpr int K1F_MAXREG = 184;
-template <int R1, typename RT, bool PART = true>
-__global__ void __maxnreg__(K1F_MAXREG)
+template <int R1, typename RT, bool PART = true, bool TMEM = false>
+__global__ void __maxnreg__(TMEM ? 168 : K1F_MAXREG)       // 168: the most three warps of a sub-partition can have
 k1f_fft_acf_mr(const K1FArgs<RT> args) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    k1f_body<R1, k1f_threads(R1), DevCtx, RT, k1f_prefetch(R1, (int)sizeof(RT)), PART>(args, smem_raw, (int)threadIdx.x, (int)blockIdx.x,
-                                                                                       (int)gridDim.x);
+    k1f_body<R1, k1f_threads(R1), DevCtx, RT, k1f_prefetch(R1, (int)sizeof(RT)), PART, TMEM>(args, smem_raw, (int)threadIdx.x,
+                                                                                             (int)blockIdx.x, (int)gridDim.x);
 }
 
 // ---------------------------------------------------------------------------

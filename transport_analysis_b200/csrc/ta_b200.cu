@@ -157,10 +157,11 @@ struct ta_ctx {
     int fast_r1 = 0;         // > 0: the plan is for the three-pass path (k1_fast.cuh) with this R1
     // debugging knobs, read from the environment ONCE when the context is created (never on a launch path):
     //   TA_B200_K1_PATH = general        the general mixed-radix FFT kernel even where the three-pass kernel applies
-    //                                    (the tests compare the two kernels with each other)
+    //                   = notmem         the three-pass kernel with its output stage through L2 even where the tensor-memory
+    //                                    build applies (the tests compare the kernels with each other)
     //   TA_B200_BULK_CHUNK = n           particles per staging chunk of ta_stage_bulk (tests: any chunking, same bits)
     //   TA_B200_HELFAND_FFT_THR = x      refinement threshold of ta_helfand_fft (scripts/helfand_fft_error_constant.py)
-    bool opt_general_fft = false;
+    bool opt_general_fft = false, opt_no_tmem = false;
     int64_t opt_bulk_chunk = 0;
     double opt_helfand_thr = -2.0;       // < -1.5: the built-in rule
     int k1_threads = 0, k1_smem = 0, k1_grid = 0;
@@ -571,7 +572,18 @@ int launch_fft_fast_r1(ta_ctx* ctx, std::vector<int>* grids) {
         void (*kern)(const K1FArgs<RT>) = k1f_fft_acf<R1, RT, PART>;
         if (smem > s.max_smem) return fail(ctx, TA_ERR_UNSUPPORTED, "three-pass FFT kernel needs more shared memory than the device has");
         int occ = 0;
-        if constexpr (NT == 320 && sizeof(RT) == 8) {
+        bool tmem = false;
+        if constexpr (PART && sizeof(RT) == 8 && (R1 == 16 || R1 == 20)) {
+            // one CTA per SM, one P1 column per thread: the output stage keeps its per-thread streams in tensor memory
+            void (*kt)(const K1FArgs<RT>) = NT == 320 ? k1f_fft_acf_mr<R1, RT, true, true> : k1f_fft_acf<R1, RT, true, true>;
+            if (!ctx->opt_no_tmem &&
+                cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess &&
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kt, NT, (size_t)smem) == cudaSuccess && occ == 1) {
+                kern = kt;
+                tmem = true;
+            } else cudaGetLastError();
+        }
+        if (!tmem) if constexpr (NT == 320 && sizeof(RT) == 8) {
             // ten FP64 warps per SM: the build with the register cap stated outright (kernels.cuh); should a compiler
             // settle above what fits, the launch-bounds build of the same kernel takes over
             cudaFuncSetAttribute(k1f_fft_acf_mr<R1, RT, PART>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -712,7 +724,10 @@ int create_common(ta_ctx* ctx, int ndev, const int* devices) {
                         "); libta_b200 has no CPU fallback");
     if (ndev < 1) return fail(ctx, TA_ERR_INVALID, "ndev must be >= 1");
     // debugging knobs (see ta_ctx): read here, once, never on a launch path
-    if (const char* v = getenv("TA_B200_K1_PATH")) ctx->opt_general_fft = std::string(v) == "general";
+    if (const char* v = getenv("TA_B200_K1_PATH")) {
+        ctx->opt_general_fft = std::string(v) == "general";
+        ctx->opt_no_tmem = std::string(v) == "notmem";
+    }
     if (const char* v = getenv("TA_B200_BULK_CHUNK")) ctx->opt_bulk_chunk = atoll(v);
     if (const char* v = getenv("TA_B200_HELFAND_FFT_THR")) ctx->opt_helfand_thr = atof(v);
     ctx->sh.resize(ndev);
