@@ -248,7 +248,8 @@ def k1_kernel_name(plan, precision="fp64"):
     rad = plan["radices"]
     rt = "double" if precision == "fp64" else "float"
     if rad[1:] == [16, 16]:
-        return f"k1f_fft_acf<{rad[0]},{rt}> (K1 three-pass radix-16 kernel, {plan['threads']} threads, bulk series prefetch)"
+        tm = ", output stage in tensor memory" if plan.get("tmem") else ""
+        return f"k1f_fft_acf<{rad[0]},{rt}> (K1 three-pass radix-16 kernel, {plan['threads']} threads, bulk series prefetch{tm})"
     return f"k1_fft_acf<{rt}> (K1 general mixed-radix kernel)"
 
 

@@ -151,6 +151,9 @@ int ta_flush_l2(ta_ctx* ctx);
 int64_t ta_launch_count(const ta_ctx* ctx);
 int ta_fft_plan_info(const ta_ctx* ctx, int* H, int* npasses, int* radices /*[12]*/,
                      int* threads, int* smem_bytes, int* grid);
+/* 1 if the last FFT-route launch kept the per-thread streams of its output stage (parked residue-0 result, particle
+ * sums, normalisation table) in tensor memory (FP64, 6,144 < T <= 10,240), else 0 */
+int ta_k1_uses_tmem(const ta_ctx* ctx);
 /* (particle, lag) pairs the last ta_helfand_fft evaluated with the exact sum (viscosity.py:212-226) because the
  * S1 - 2 S2 difference was not good to 1e-10 there; -1: the direct kernel took over the whole call. */
 int64_t ta_helfand_fft_refined(const ta_ctx* ctx);

@@ -328,7 +328,7 @@ def test_tensor_memory_output_stage_vs_global_one_and_across_launches(T, N, dim,
     vel, _ = random_trajectory(T, N, seed=T + N, rho=0.7)
     u = make_universe(None, vel)
     v = VACF(u.atoms, dim_type=dim, fft=True).run()
-    assert v._ctx.fft_plan_info()["radices"][0] in (16, 20)
+    assert v._ctx.fft_plan_info()["radices"][0] in (16, 20) and v._ctx.fft_plan_info()["tmem"]
     cols, _ = oracle.parse_dim_type(dim)
     ref_bp, _ = oracle.vacf_fft(_f64(vel)[:, :4, cols])
     assert_close_normwise(v.results.vacf_by_particle[:, :4], ref_bp, TOL64, "tensor-memory build vs oracle")
@@ -342,6 +342,7 @@ def test_tensor_memory_output_stage_vs_global_one_and_across_launches(T, N, dim,
     monkeypatch.delenv("TA_B200_BULK_CHUNK")
     monkeypatch.setenv("TA_B200_K1_PATH", "notmem")
     g = VACF(u.atoms, dim_type=dim, fft=True).run()
+    assert not g._ctx.fft_plan_info()["tmem"]
     assert np.array_equal(g.results.vacf_by_particle, v.results.vacf_by_particle)
     assert np.array_equal(g.results.timeseries, v.results.timeseries)
 

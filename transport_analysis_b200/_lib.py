@@ -48,6 +48,7 @@ _SIGNATURES = {
     "ta_last_kernel_ms": (c_int, [c_void_p, POINTER(c_float)]),
     "ta_probe_fp64": (c_int, [c_void_p, POINTER(c_double)]),
     "ta_probe_h2d": (c_int, [c_void_p, c_uint64, POINTER(c_double)]),
+    "ta_k1_uses_tmem": (c_int, [c_void_p]),
     "ta_flush_l2": (c_int, [c_void_p]),
     "ta_launch_count": (c_int64, [c_void_p]),
     "ta_helfand_fft_refined": (c_int64, [c_void_p]),
@@ -307,7 +308,7 @@ class Context:
         self._lib.ta_fft_plan_info(self._h, ctypes.byref(H), ctypes.byref(npz), rad, ctypes.byref(thr),
                                    ctypes.byref(smem), ctypes.byref(grid))
         return {"H": H.value, "radices": list(rad)[: npz.value], "threads": thr.value,
-                "smem_bytes": smem.value, "grid": grid.value}
+                "smem_bytes": smem.value, "grid": grid.value, "tmem": bool(self._lib.ta_k1_uses_tmem(self._h))}
 
 
 def host_register(arr: np.ndarray):

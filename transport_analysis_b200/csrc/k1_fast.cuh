@@ -121,7 +121,7 @@ TA_HD void k1f_p1_twiddles(C om, int r, C* e, C* g) {
 template <int R1, int NT, class Ctx, typename RT, bool PREF, bool PART = true, bool TMEM = false>
 TA_HD void k1f_body(const K1FArgs<RT>& A, unsigned char* smem_raw, int tid, int bid, int nblk) {
     using C = cplx<RT>;
-    static_assert(!TMEM || (PART && PREF && sizeof(RT) == 8 && NT >= 256 && R1 % 4 == 0 && 12 * R1 <= 256),
+    static_assert(!TMEM || (PREF && sizeof(RT) == 8 && NT >= 256 && R1 % 4 == 0 && 12 * R1 <= 256),
                   "tensor-memory build: FP64, one P1 column per thread, three 4 R1-column arrays in a 256-column half");
     constexpr int H = 256 * R1;
     constexpr int NV = 16 * R1;          // radix-16 butterflies per pass ("virtual threads")
@@ -161,7 +161,7 @@ TA_HD void k1f_body(const K1FArgs<RT>& A, unsigned char* smem_raw, int tid, int 
                     sc[i] = z[i];
                     if (n < nh) { const C v = inv2i[n]; sc[i] = cmake<double>((double)v.x, (double)v.y); }   // 0 beyond the series: nothing is added there
                 }
-                Ctx::tmem_st4(tm + TM_PART + 16 * c, z);
+                if (PART) Ctx::tmem_st4(tm + TM_PART + 16 * c, z);
                 Ctx::tmem_st4(tm + TM_INV + 16 * c, sc);
             });
             Ctx::tmem_wait_st();
@@ -385,13 +385,15 @@ TA_HD void k1f_body(const K1FArgs<RT>& A, unsigned char* smem_raw, int tid, int 
                                 x[4 * c + i] = cmake<RT>(x[4 * c + i].x * (RT)t[i].x, x[4 * c + i].y * (RT)t[i].y);
                                 if (n < nh) row[n] = cmake<double>((double)x[4 * c + i].x, (double)x[4 * c + i].y);
                             }
-                            Ctx::tmem_ld4(tm + TM_PART + 16 * c, t);             // particle sums
+                            if (PART) {
+                                Ctx::tmem_ld4(tm + TM_PART + 16 * c, t);         // particle sums
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const int n = j + 256 * (4 * c + i);
-                                if (n < nh) t[i] = cmake<double>(t[i].x + (double)x[4 * c + i].x, t[i].y + (double)x[4 * c + i].y);
+                                for (int i = 0; i < 4; ++i) {
+                                    const int n = j + 256 * (4 * c + i);
+                                    if (n < nh) t[i] = cmake<double>(t[i].x + (double)x[4 * c + i].x, t[i].y + (double)x[4 * c + i].y);
+                                }
+                                Ctx::tmem_st4(tm + TM_PART + 16 * c, t);
                             }
-                            Ctx::tmem_st4(tm + TM_PART + 16 * c, t);
                         });
                         Ctx::tmem_wait_st();
                     }
@@ -446,7 +448,7 @@ TA_HD void k1f_body(const K1FArgs<RT>& A, unsigned char* smem_raw, int tid, int 
         // add the particle sums of this launch to the CTA's global partial row (the host zeroed it before the first launch
         // of the compute call; a call that follows ta_stage_bulk launches once per staging chunk), then give the tensor
         // memory back
-        if (tid < 256) {
+        if (PART && tid < 256) {
             static_for<0, R1 / 4>([&](auto ic) {
                 constexpr int c = decltype(ic)::value;
                 cd ps[4];

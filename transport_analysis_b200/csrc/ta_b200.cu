@@ -165,6 +165,7 @@ struct ta_ctx {
     int64_t opt_bulk_chunk = 0;
     double opt_helfand_thr = -2.0;       // < -1.5: the built-in rule
     int k1_threads = 0, k1_smem = 0, k1_grid = 0;
+    bool k1_tmem = false;    // the last K1 launch kept its output-stage streams in tensor memory
     bool have_mean = false;  // ts_mean of the first shard holds the result of a compute call
     int64_t launches = 0;
     long long helfand_fft_flagged = 0;   // (particle, lag) pairs the last ta_helfand_fft evaluated exactly; -1: all (K3 took over)
@@ -554,7 +555,7 @@ int launch_fft(ta_ctx* ctx, std::vector<int>* grids) {
         }
         CK(cudaEventRecord(s.ev_kb, s.s_compute));
         s.kernel_timed = true;
-        ctx->k1_threads = nthr; ctx->k1_smem = (int)dyn; ctx->k1_grid = grid;
+        ctx->k1_threads = nthr; ctx->k1_smem = (int)dyn; ctx->k1_grid = grid; ctx->k1_tmem = false;
     }
     return TA_OK;
 }
@@ -573,9 +574,9 @@ int launch_fft_fast_r1(ta_ctx* ctx, std::vector<int>* grids) {
         if (smem > s.max_smem) return fail(ctx, TA_ERR_UNSUPPORTED, "three-pass FFT kernel needs more shared memory than the device has");
         int occ = 0;
         bool tmem = false;
-        if constexpr (PART && sizeof(RT) == 8 && (R1 == 16 || R1 == 20)) {
+        if constexpr (sizeof(RT) == 8 && (R1 == 16 || R1 == 20)) {
             // one CTA per SM, one P1 column per thread: the output stage keeps its per-thread streams in tensor memory
-            void (*kt)(const K1FArgs<RT>) = NT == 320 ? k1f_fft_acf_mr<R1, RT, true, true> : k1f_fft_acf<R1, RT, true, true>;
+            void (*kt)(const K1FArgs<RT>) = NT == 320 ? k1f_fft_acf_mr<R1, RT, PART, true> : k1f_fft_acf<R1, RT, PART, true>;
             if (!ctx->opt_no_tmem &&
                 cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess &&
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kt, NT, (size_t)smem) == cudaSuccess && occ == 1) {
@@ -615,7 +616,7 @@ int launch_fft_fast_r1(ta_ctx* ctx, std::vector<int>* grids) {
         }
         CK(cudaEventRecord(s.ev_kb, s.s_compute));
         s.kernel_timed = true;
-        ctx->k1_threads = NT; ctx->k1_smem = smem; ctx->k1_grid = grid;
+        ctx->k1_threads = NT; ctx->k1_smem = smem; ctx->k1_grid = grid; ctx->k1_tmem = tmem;
     }
     return TA_OK;
 }
@@ -1411,5 +1412,7 @@ int ta_fft_plan_info(const ta_ctx* ctx, int* H, int* npasses, int* radices, int*
     if (grid) *grid = ctx->k1_grid;
     return TA_OK;
 }
+
+int ta_k1_uses_tmem(const ta_ctx* ctx) { return ctx && ctx->k1_tmem ? 1 : 0; }
 
 }  // extern "C"
