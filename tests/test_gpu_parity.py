@@ -618,6 +618,29 @@ def test_helfand_fft_route_against_exact_route(rand_u, dim, n_dim):
     assert_allclose(fast.results.visc_by_particle, ref_bp, rtol=TOL64)
 
 
+@pytest.mark.parametrize("T,N,dim", [(10000, 310, "xyz"), (7000, 200, "xy")])
+def test_helfand_fft_route_on_the_tensor_memory_kernel(T, N, dim):
+    """ta_helfand_fft at lengths whose K1 is the R1 = 16 / 20 build: K1 runs WITHOUT particle sums (K5 forms its own) and
+    with its output stage in tensor memory (parked residue-0 result + normalisation table).  Against the direct route on
+    every (lag, particle) and against the oracle on sampled particles."""
+    vel, pos = random_trajectory(T, N, seed=T + N, with_positions=True, rho=0.9)
+    masses = np.random.default_rng(1).choice([1.008, 12.011, 15.999], N)
+    u = make_universe(pos, vel, masses=masses, dimensions=BOX)
+    exact = VH(u.atoms, dim_type=dim, fft=False).run()
+    fast = VH(u.atoms, dim_type=dim, fft=True).run()
+    plan = fast._ctx.fft_plan_info()
+    assert plan["radices"][0] in (16, 20) and plan["tmem"] and fast._ctx.helfand_fft_refined() >= 0
+    assert_allclose(fast.results.timeseries, exact.results.timeseries, rtol=TOL64)
+    assert_allclose(fast.results.visc_by_particle[1:], exact.results.visc_by_particle[1:], rtol=TOL64)
+    assert np.all(fast.results.visc_by_particle[0] == 0.0)
+    cols, _ = oracle.parse_dim_type(dim)
+    pick = [0, N // 2, N - 1]
+    lags = np.array([1, 2, 17, T // 3, T // 2, T - 2, T - 1])
+    vol = np.full(T, float(np.prod(np.float32(BOX[:3]).astype(np.float64))))
+    ref_bp, _ = oracle.helfand_msd(_f64(vel)[:, pick][:, :, cols], _f64(pos)[:, pick][:, :, cols], masses[pick], vol, 300.0, lags=lags)
+    assert_allclose(fast.results.visc_by_particle[lags][:, pick], ref_bp[lags], rtol=TOL64)
+
+
 def test_helfand_default_is_the_direct_route(rand_u):
     """the O(T log T) route is opt-in; ViscosityHelfand(ag) runs the reference's direct sums (K3)."""
     u = rand_u[0]
